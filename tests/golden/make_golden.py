@@ -1,0 +1,210 @@
+#!/usr/bin/env python
+"""Generates tests/golden/*.npz by running the LIVE reference (/root/reference).
+
+Run in the build container only (the reference does not exist on the GPU box):
+
+    python tests/golden/make_golden.py
+
+The reference has no tests or golden vectors of its own, so
+these fixtures -- outputs of the unmodified reference functions under a fixed
+``np.random.seed`` -- are what pins the oracle and the CUDA path.  The reference
+imports ``statsmodels`` at pangenome_analysis.py:18 but only uses it at :380 (off the
+hot path); it is absent from this image, so an empty module is registered in
+``sys.modules`` before the import.  Nothing else is patched.
+
+Versions at generation time are recorded in tests/golden/MANIFEST.json.
+"""
+import contextlib
+import hashlib
+import io
+import json
+import os
+import sys
+import types
+import warnings
+
+import numpy as np
+import pandas as pd
+import scipy
+import scipy.sparse
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+REPO = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, REPO)
+sys.dont_write_bytecode = True
+sys.path.insert(0, "/root/reference")
+for name in ("statsmodels", "statsmodels.stats"):
+    sys.modules.setdefault(name, types.ModuleType(name))
+
+import pangenomix.pangenome_analysis as ref_pa  # noqa: E402  (the reference)
+import pangenomix.sparse_utils as ref_su  # noqa: E402
+
+from pangenomix_b200 import synth  # noqa: E402
+
+
+def quiet(fn, *args, **kwargs):
+    with contextlib.redirect_stdout(io.StringIO()), warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        return fn(*args, **kwargs)
+
+
+def matrix_digest(coo):
+    coo = scipy.sparse.coo_matrix(coo)
+    order = np.lexsort((coo.col, coo.row))
+    h = hashlib.sha256()
+    h.update(np.asarray(coo.shape, dtype=np.int64).tobytes())
+    h.update(coo.row[order].astype(np.int32).tobytes())
+    h.update(coo.col[order].astype(np.int32).tobytes())
+    h.update(coo.data[order].astype(np.int64).tobytes())
+    return h.hexdigest()
+
+
+def lsdf_of(coo):
+    index, columns = synth.labels_for(*coo.shape)
+    return ref_su.LightSparseDataFrame(index, columns, coo)
+
+
+def run_curves(coo, seed, num_iter):
+    """Reference curves + the permutations the reference consumed for them."""
+    np.random.seed(seed)
+    df = quiet(ref_pa.estimate_pan_core_size, lsdf_of(coo), num_iter)
+    np.random.seed(seed)
+    n = coo.shape[1]
+    perms = np.empty((num_iter, n), dtype=np.int64)
+    for i in range(num_iter):
+        a = np.arange(n)
+        np.random.shuffle(a)
+        perms[i] = a
+    assert df.values.dtype == np.float64
+    assert list(df.index) == ["Iter%d" % (i + 1) for i in range(num_iter)]
+    assert list(df.columns) == ["Pan%d" % (i + 1) for i in range(n)] + \
+        ["Core%d" % (i + 1) for i in range(n)]
+    return df, perms
+
+
+def save_curve_case(name, coo, seed, num_iter, store_matrix=True, heaps=False):
+    coo = scipy.sparse.coo_matrix(coo)
+    df, perms = run_curves(coo, seed, num_iter)
+    out = {
+        "shape": np.asarray(coo.shape, dtype=np.int64),
+        "seed": np.int64(seed),
+        "num_iter": np.int64(num_iter),
+        "curves": df.values.astype(np.int32),
+        "digest": np.array(matrix_digest(coo)),
+    }
+    assert np.array_equal(out["curves"].astype(np.float64), df.values)
+    if store_matrix:
+        out["row"] = coo.row.astype(np.int32)
+        out["col"] = coo.col.astype(np.int32)
+        out["data"] = coo.data.astype(np.int64)
+    if perms.shape[1] <= 64:
+        out["perms"] = perms.astype(np.int32)
+    if heaps:
+        mean_df = pd.DataFrame([df.mean()], columns=df.columns)   # plot.py:8-11
+        out["mean"] = mean_df.values[0]
+        out["heaps_mean"] = quiet(ref_pa.fit_heaps_by_iteration, mean_df).values[0]
+        out["heaps_iter"] = quiet(ref_pa.fit_heaps_by_iteration, df.iloc[:min(num_iter, 8)]).values
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    print("wrote", name, coo.shape, "nnz", coo.nnz, "iters", num_iter)
+
+
+def edge_matrix():
+    """500 x 37 with all-present, empty, single-present, single-absent and duplicate rows."""
+    rng = np.random.RandomState(99)
+    x = (rng.random_sample((500, 37)) < rng.beta(0.4, 0.4, size=(500, 1))).astype(np.int64)
+    x[0:10] = 1                       # all-present
+    x[10:20] = 0                      # empty
+    x[20:40] = 0
+    x[np.arange(20, 40), rng.randint(37, size=20)] = 1      # singletons
+    x[40:60] = 1
+    x[np.arange(40, 60), rng.randint(37, size=20)] = 0      # single-absent
+    x[60:70] = x[70:80]               # identical rows
+    return scipy.sparse.coo_matrix(x)
+
+
+def main():
+    manifest = {
+        "numpy": np.__version__, "scipy": scipy.__version__, "pandas": pd.__version__,
+        "python": sys.version.split()[0],
+        "reference": "/root/reference/pangenomix (AnnaLew/pangenomix, unmodified; statsmodels stubbed)",
+    }
+    # 1. the survey's known-answer matrix
+    kat = np.array([[1, 1, 1, 1, 1], [1, 0, 1, 1, 1], [0, 0, 1, 0, 0],
+                    [1, 1, 0, 0, 0], [0, 0, 0, 0, 1], [0, 1, 1, 0, 1]], dtype=np.int64)
+    save_curve_case("kat_6x5", scipy.sparse.coo_matrix(kat), 12345, 3, heaps=True)
+    # 2. small synthetic, two seeds
+    small = synth.bernoulli_matrix(800, 50, 450, seed=7)
+    save_curve_case("synth_800x50_s0", small, 0, 10, heaps=True)
+    save_curve_case("synth_800x50_s1", small, 1, 10)
+    # 3. edge rows
+    save_curve_case("edge_500x37", edge_matrix(), 1, 20)
+    # 4. tiny shapes
+    for n in (1, 2, 3, 4):
+        rng = np.random.RandomState(n)
+        x = (rng.random_sample((40, n)) < 0.5).astype(np.int64)
+        save_curve_case("tiny_40x%d" % n, scipy.sparse.coo_matrix(x), 5, 6)
+    # 5. config C1 in full (matrix regenerated by synth in the tests; digest stored)
+    c1 = synth.config_matrix("c1")
+    save_curve_case("c1_8000x50", c1, 12345, 100, store_matrix=False, heaps=True)
+    # 6. a 4000 x 400 table shaped like a slice of C2
+    c2s = synth.bernoulli_matrix(4000, 400, 450, seed=20242)
+    save_curve_case("c2slice_4000x400", c2s, 12345, 5, store_matrix=False, heaps=True)
+    # 7. duplicates in the COO are summed by .tocsr() (:75): pan unaffected, core changes
+    dup = scipy.sparse.coo_matrix(
+        (np.ones(9, dtype=np.int64),
+         (np.array([0, 0, 0, 1, 1, 2, 2, 2, 2]), np.array([0, 0, 1, 1, 2, 0, 1, 2, 3]))),
+        shape=(3, 4))
+    df, perms = run_curves(dup, 3, 4)
+    np.savez_compressed(os.path.join(HERE, "dup_3x4.npz"), row=dup.row.astype(np.int32),
+                        col=dup.col.astype(np.int32), data=dup.data.astype(np.int64),
+                        shape=np.asarray(dup.shape, dtype=np.int64), perms=perms.astype(np.int32),
+                        curves=df.values.astype(np.int32), seed=np.int64(3), num_iter=np.int64(4))
+    print("wrote dup_3x4")
+
+    # 8. Bernoulli grid: likelihood, gradient, full fit
+    x, p_true, q_true = synth.bernoulli_grid_matrix(300, 40, seed=3)
+    n_genes, n_genomes = x.shape
+    lo, hi = 0.8, 0.99999999
+    p0 = np.clip(x.sum(axis=1) / float(n_genomes), lo, hi)
+    q0 = np.clip(0.9999 * np.ones(n_genomes), lo, hi)
+    rng = np.random.RandomState(11)
+    p1 = rng.uniform(lo, hi, size=n_genes)
+    q1 = rng.uniform(lo, hi, size=n_genomes)
+    ll = ref_pa.__dict__["__bernoulli_grid_loglikelihood__"]
+    grad = ref_pa.__dict__["__bernoulli_grid_loglikelihood_gradient__"]
+    index, columns = synth.labels_for(n_genes, n_genomes)
+    dense = pd.DataFrame(x, index=index, columns=columns)
+    df_opt, res = quiet(ref_pa.compute_bernoulli_grid_core_genome, dense)
+    assert list(df_opt.columns) == ["initial", "optimum"]
+    assert list(df_opt.index) == ["Loglikelihood"] + ["p_" + s for s in index] + ["q_" + s for s in columns]
+    x2 = kat[:2].astype(np.float64)
+    np.savez_compressed(
+        os.path.join(HERE, "bernoulli_300x40.npz"),
+        x=x.astype(np.uint8), p0=p0, q0=q0, p1=p1, q1=q1,
+        ll0=np.float64(ll(x, p0, q0)), grad0=grad(x, p0, q0),
+        ll1=np.float64(ll(x, p1, q1)), grad1=grad(x, p1, q1),
+        fit_initial=df_opt["initial"].values, fit_optimum=df_opt["optimum"].values,
+        fit_x=res.x, fit_fun=np.float64(res.fun), fit_nit=np.int64(res.nit),
+        fit_nfev=np.int64(res.nfev), fit_message=np.array(str(res.message)),
+        kat_x=x2, kat_p=np.array([0.99999999, 0.8]), kat_q=0.9999 * np.ones(5),
+        kat_ll=np.float64(ll(x2, np.array([0.99999999, 0.8]), 0.9999 * np.ones(5))),
+        kat_grad=grad(x2, np.array([0.99999999, 0.8]), 0.9999 * np.ones(5)))
+    print("wrote bernoulli_300x40: init LL", df_opt["initial"].values[0], "opt LL", -res.fun,
+          "nit", res.nit)
+
+    # 9. LSDF .npz round trip as the reference writes it (sparse_utils.py:295-314)
+    tmp = os.path.join(HERE, "lsdf_small.npz")
+    lsdf = lsdf_of(small)
+    lsdf.to_npz(tmp)
+    back = ref_su.read_lsdf(tmp)
+    assert (back.data != lsdf.data).nnz == 0
+    manifest["lsdf_small_row_sums_head"] = [int(v) for v in lsdf.sum(axis="index")[:8]]
+    manifest["lsdf_small_col_sums_head"] = [int(v) for v in lsdf.sum(axis="columns")[:8]]
+    print("wrote lsdf_small.npz (+ .labels.txt) with the reference's own writer")
+
+    with open(os.path.join(HERE, "MANIFEST.json"), "w") as f:
+        json.dump(manifest, f, indent=1, sort_keys=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,102 @@
+"""The oracle against the fixtures produced by the live reference (tests/golden/make_golden.py)."""
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse
+
+import oracle
+from conftest import CURVE_CASES, draw_perms, golden_matrix, load_golden
+
+
+@pytest.mark.parametrize("name", CURVE_CASES)
+def test_minrank_matches_reference(name):
+    g = load_golden(name)
+    coo = golden_matrix(name, g)
+    perms = draw_perms(int(g["seed"]), coo.shape[1], int(g["num_iter"]))
+    pan, core = oracle.pan_core_curves_minrank(coo, perms)
+    assert np.array_equal(np.hstack([pan, core]), g["curves"].astype(np.float64))
+
+
+@pytest.mark.parametrize("name", [c for c in CURVE_CASES if c != "c1_8000x50"])
+def test_direct_matches_reference(name):
+    g = load_golden(name)
+    coo = golden_matrix(name, g)
+    num_iter = min(int(g["num_iter"]), 4)
+    perms = draw_perms(int(g["seed"]), coo.shape[1], num_iter)
+    pan, core = oracle.pan_core_curves_direct(coo, perms)
+    assert np.array_equal(np.hstack([pan, core]), g["curves"][:num_iter].astype(np.float64))
+
+
+def test_stored_perms_are_the_numpy_stream():
+    g = load_golden("kat_6x5")
+    assert np.array_equal(draw_perms(12345, 5, 3), g["perms"])
+    assert g["perms"].tolist() == [[0, 4, 3, 1, 2], [3, 0, 2, 1, 4], [4, 0, 3, 1, 2]]
+
+
+def test_survey_kat_values():
+    g = load_golden("kat_6x5")
+    assert g["curves"][:, :5].tolist() == [[3, 5, 5, 5, 6], [2, 3, 5, 5, 6], [4, 5, 5, 5, 6]]
+    assert g["curves"][:, 5:].tolist() == [[3, 2, 2, 1, 1], [2, 2, 2, 1, 1], [4, 2, 2, 1, 1]]
+    np.testing.assert_allclose(g["heaps_mean"], [0.385038, 3.155842], rtol=1e-5)
+
+
+def test_duplicates_are_summed_like_the_reference():
+    g = load_golden("dup_3x4")
+    coo = scipy.sparse.coo_matrix((g["data"], (g["row"], g["col"])), shape=tuple(g["shape"]))
+    pan, core = oracle.pan_core_curves_direct(coo, g["perms"])
+    assert np.array_equal(np.hstack([pan, core]), g["curves"].astype(np.float64))
+    with pytest.raises(ValueError):
+        oracle.pan_core_curves_minrank(coo, g["perms"])
+
+
+def test_end_to_end_frame_and_rng_consumption():
+    g = load_golden("synth_800x50_s0")
+    coo = golden_matrix("synth_800x50_s0", g)
+
+    class Holder:
+        shape = coo.shape
+        data = coo
+
+    np.random.seed(0)
+    df = oracle.estimate_pan_core_size_minrank(Holder, 10)
+    after = np.random.random_sample()
+    assert df.values.dtype == np.float64
+    assert np.array_equal(df.values, g["curves"].astype(np.float64))
+    assert df.index[0] == "Iter1" and df.columns[0] == "Pan1" and df.columns[-1] == "Core50"
+    np.random.seed(0)
+    draw_perms_state = [np.random.shuffle(np.arange(50)) for _ in range(10)]
+    assert after == np.random.random_sample()
+    del draw_perms_state
+
+
+@pytest.mark.parametrize("name", ["kat_6x5", "synth_800x50_s0", "c1_8000x50", "c2slice_4000x400"])
+def test_mean_and_heaps(name):
+    g = load_golden(name)
+    n = int(g["shape"][1])
+    cols = ["Pan%d" % (i + 1) for i in range(n)] + ["Core%d" % (i + 1) for i in range(n)]
+    df = pd.DataFrame(g["curves"].astype(np.float64), columns=cols,
+                      index=["Iter%d" % (i + 1) for i in range(g["curves"].shape[0])])
+    mean = oracle.calculate_mean(df)
+    assert np.array_equal(mean.values[0], g["mean"])
+    fit = oracle.fit_heaps_by_iteration(mean)
+    assert list(fit.columns) == ["alpha", "kappa"]
+    np.testing.assert_allclose(fit.values[0], g["heaps_mean"], rtol=1e-12)
+
+
+@pytest.mark.parametrize("n", [2, 7, 50, 400])
+def test_legacy_shuffle_emulation(n):
+    got = oracle.legacy_shuffle_stream(12345, n, 3)
+    assert np.array_equal(got, draw_perms(12345, n, 3))
+
+
+def test_bernoulli_ll_grad():
+    g = load_golden("bernoulli_300x40")
+    x = g["x"].astype(np.float64)
+    for tag in ("0", "1"):
+        p, q = g["p" + tag], g["q" + tag]
+        np.testing.assert_allclose(oracle.bernoulli_ll(x, p, q), g["ll" + tag], rtol=1e-13)
+        np.testing.assert_allclose(oracle.bernoulli_grad(x, p, q), g["grad" + tag], rtol=1e-12)
+    np.testing.assert_allclose(oracle.bernoulli_ll(g["kat_x"], g["kat_p"], g["kat_q"]),
+                               -2.502512292672613, rtol=1e-13)
+    np.testing.assert_allclose(oracle.bernoulli_grad(g["kat_x"], g["kat_p"], g["kat_q"]),
+                               g["kat_grad"], rtol=1e-13)
