@@ -1,0 +1,399 @@
+#!/usr/bin/env python
+"""bench.py -- pan/core permutations per second on B200 (BASELINE.json's metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c1] [--perms P]
+    python bench.py --impl reference ...          # the CPU arm (oracle C port, all host threads)
+    torchrun --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU
+
+A step is one pass of the hot path over one batch of permutations: P genome orders
+(per GPU) -> P pan/core curves, through libpgx_b200 (include/pgx.h).  The default workload
+is config C4 of BASELINE.json (10,000 genomes x 200,000 genes, 10,000 permutations), the
+configuration the north_star's roofline and scaling targets are quoted on.
+
+  value : permutations/s, table and permutations resident in HBM, CUDA-event timed,
+          max over ranks (weak scaling: every rank rarefies its own P permutations of the
+          replicated table; for N > 1 the curves are gathered to rank 0 over NCCL inside
+          the timed region).
+  e2e   : the same through the host-buffer C-ABI call (pinned host permutations in,
+          host curves out; copies inside the timed region).
+  roofline : row kernel only, algorithmic bytes of SURVEY.md section 8d
+          (4 nnz + 4 (G + 1) per permutation) over its CUDA-event duration, against the
+          measured HBM copy bandwidth of MEASURED_PEAKS.json.
+  cpu_baseline : the oracle's C port of the reference algorithm on a bounded sample.
+One JSON line on stdout (rank 0).
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "pan_core_permutations_per_sec"
+UNIT = "perms/s"
+FALLBACK_HBM_GBS = 6650.0        # /opt/skills/guides/B200_PROFILING.md fallback
+
+
+def log(*a):
+    print(*a, file=sys.stderr, flush=True)
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c4"])
+    ap.add_argument("--perms", type=int, default=0, help="permutations per GPU per step (0 = the config's)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+# --------------------------------------------------------------------------------------
+# workload
+# --------------------------------------------------------------------------------------
+def load_matrix(name, rank, barrier):
+    """Synthetic table of SURVEY.md section 8d; generated once per box and cached in /tmp."""
+    import scipy.sparse
+    from pangenomix_b200 import synth
+    n_genes, n_genomes, _, seed, _ = synth.CONFIGS[name]
+    cache = os.path.join(tempfile.gettempdir(), "pgx_synth_%s_%d.npy" % (name, seed))
+    if rank == 0 and not os.path.exists(cache):
+        t = time.time()
+        coo = synth.config_matrix(name)
+        packed = np.stack([coo.row.astype(np.int32), coo.col.astype(np.int32)])
+        tmp = cache + ".tmp%d.npy" % os.getpid()
+        np.save(tmp, packed)
+        os.replace(tmp, cache)
+        log("[bench] generated %s %s nnz=%d in %.1fs" % (name, coo.shape, coo.nnz, time.time() - t))
+    barrier()
+    packed = np.load(cache)
+    data = np.ones(packed.shape[1], dtype=np.int64)
+    return scipy.sparse.coo_matrix((data, (packed[0], packed[1])), shape=(n_genes, n_genomes))
+
+
+def workload_config(name, coo, perms, world):
+    return {
+        "workload": "%s: estimate_pan_core_size on a synthetic %d-genome x %d-gene presence/absence "
+                    "table (nnz %d), %d permutations per GPU per step" % (
+                        name.upper(), coo.shape[1], coo.shape[0], coo.nnz, perms),
+        "n_genomes": int(coo.shape[1]), "n_genes": int(coo.shape[0]), "nnz": int(coo.nnz),
+        "perms_per_gpu": int(perms), "parallelism": "permutation shards x%d, table replicated" % world,
+    }
+
+
+# --------------------------------------------------------------------------------------
+# CPU arm (oracle C port)
+# --------------------------------------------------------------------------------------
+def cpu_sample(coo, n_genomes, budget_s, threads):
+    """Times the C port of pangenome_analysis.py:81-90 on a bounded sample of permutations."""
+    from oracle import cport
+    gm = cport.GenomeMajor(coo)
+    rng = np.random.RandomState(1)
+    one = np.stack([rng.permutation(n_genomes)]).astype(np.int32)
+    t = time.perf_counter()
+    cport.curves_direct(gm, one, n_threads=1)
+    t1 = time.perf_counter() - t
+    per_thread = max(1, int(round(budget_s / max(t1, 1e-6))))
+    sample = threads * per_thread
+    perms = np.stack([rng.permutation(n_genomes) for _ in range(sample)]).astype(np.int32)
+    return gm, perms, t1
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    from oracle import build as oracle_build, cport
+    oracle_build.build()
+    from pangenomix_b200 import synth
+    coo = load_matrix(args.workload, 0, lambda: None)
+    perms_cfg = args.perms or synth.CONFIGS[args.workload][4]
+    threads = os.cpu_count() or 1
+    gm, perms, t1 = cpu_sample(coo, coo.shape[1], max(1.0, args.cpu_seconds / 4.0), threads)
+    for _ in range(args.warmup):
+        cport.curves_direct(gm, perms[:threads], n_threads=threads)
+    t = time.perf_counter()
+    for _ in range(args.steps):
+        cport.curves_direct(gm, perms, n_threads=threads)
+    dt = time.perf_counter() - t
+    value = perms.shape[0] * args.steps / dt
+    sample = "%d permutations per step (of the config's %d), %d threads, oracle C port of " \
+             "pangenome_analysis.py:81-90" % (perms.shape[0], perms_cfg, threads)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": dt / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "int64",
+        "data": "synthetic", "config": workload_config(args.workload, coo, perms_cfg, world),
+        "cells_per_s": value * coo.shape[0] * coo.shape[1],
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "single_thread_s_per_perm": t1},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    FIELDS = ["clocks.sm", "clocks.max.sm", "power.draw",
+              "clocks_event_reasons.hw_slowdown", "clocks_event_reasons.hw_thermal_slowdown",
+              "clocks_event_reasons.sw_thermal_slowdown", "clocks_event_reasons.sw_power_cap"]
+
+    def __init__(self, index):
+        self.rows = []
+        self.proc = None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", "-i", str(index), "--query-gpu=" + ",".join(self.FIELDS),
+                 "--format=csv,noheader,nounits", "-lms", "50"],
+                stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append((time.perf_counter(), line.strip()))
+
+    def window(self, t0, t1):
+        sm, sm_max, power, reasons = [], 0.0, 0.0, set()
+        for t, line in self.rows:
+            if t < t0 or t > t1 + 0.05:
+                continue
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) != len(self.FIELDS):
+                continue
+            try:
+                sm.append(float(parts[0]))
+                sm_max = max(sm_max, float(parts[1]))
+                power = max(power, float(parts[2]))
+            except ValueError:
+                continue
+            for name, flag in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                  parts[3:]):
+                if flag == "Active":
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": sm_max or None,
+                "power_w_max": power or None, "samples": len(sm), "reasons": sorted(reasons)}
+
+    def stop(self):
+        if self.proc is not None:
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=2)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+
+def measured_peak():
+    path = os.path.join(REPO, "MEASURED_PEAKS.json")
+    try:
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except (OSError, KeyError, ValueError):
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
+
+
+def ncu_traffic(workload):
+    """DRAM bytes per row-kernel launch from the committed ncu capture, if there is one."""
+    try:
+        with open(os.path.join(REPO, "profiles", "roofline_traffic.json")) as f:
+            return json.load(f).get(workload)
+    except (OSError, ValueError):
+        return None
+
+
+# --------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------
+def run_b200(args, rank, world, local_rank):
+    import torch
+    import torch.distributed as dist
+    from pangenomix_b200 import _native, engine, synth
+    from pangenomix_b200 import build as pgx_build
+
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local_rank)
+    device = torch.device("cuda", local_rank)
+    if rank == 0:
+        pgx_build.build()
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+
+    barrier()
+    _native.load()
+    coo = load_matrix(args.workload, rank, barrier)
+    n_genes, n = coo.shape
+    perms_n = args.perms or synth.CONFIGS[args.workload][4]
+    t = time.time()
+    eng = engine.PanCoreEngine(coo, device=device)
+    hp = eng.host_plan
+    log("[bench r%d] plan: %d folded rows, %d tasks, folded nnz %d (%.2fx fewer than nnz), %.1fs" % (
+        rank, hp.n_rows, hp.n_tasks, hp.folded_nnz, hp.nnz / max(1, hp.folded_nnz), time.time() - t))
+
+    # every rank rarefies its own permutations (numpy legacy stream, seed 12345 + rank)
+    h_perms, h_perms_owner = engine.pinned_empty((perms_n, n), np.uint16)
+    np.random.seed(12345 + rank)
+    t = time.time()
+    engine.draw_legacy_permutations(n, perms_n, out=h_perms)
+    host_rng_s = time.time() - t
+    d_perms = torch.empty((perms_n, n), dtype=torch.int16, device=device)
+    d_perms.copy_(h_perms_owner)
+    d_out = torch.empty((perms_n, 2 * n), dtype=torch.int32, device=device)
+    gather_list = None
+    if world > 1 and rank == 0:
+        gather_list = [torch.empty_like(d_out) for _ in range(world)]
+
+    def step():
+        eng.curves_device(d_perms, out=d_out)
+        if world > 1:
+            dist.gather(d_out, gather_list=gather_list, dst=0)
+
+    for _ in range(max(args.warmup, 3)):
+        step()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    time.sleep(0.2)
+    _native.profile_read()
+    _native.profile_enable(True)
+    launches0 = _native.launch_count()
+    barrier()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    w0 = time.perf_counter()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    torch.cuda.synchronize()
+    w1 = time.perf_counter()
+    barrier()
+    ms = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+    ms_total = float(ms.item())
+    launches = _native.launch_count() - launches0
+    row_ms, scan_ms, calls = _native.profile_read()
+    _native.profile_enable(False)
+    clocks = sampler.window(w0, w1) if sampler else None
+
+    # parity guard on the timed output (size-independent invariants, cheap)
+    curves = d_out[:64].cpu().numpy()
+    assert np.all(np.diff(curves[:, :n], axis=1) >= 0) and np.all(np.diff(curves[:, n:], axis=1) <= 0)
+    assert np.array_equal(curves[:, 0], curves[:, n])
+
+    # ---- end to end through the host-buffer C-ABI call ----
+    e2e = None
+    if not args.no_e2e:
+        h_out, h_out_owner = engine.pinned_empty((perms_n, 2 * n), np.int32)
+        for _ in range(2):
+            eng.curves_host(h_perms, out=h_out)
+        barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            eng.curves_host(h_perms, out=h_out)
+        torch.cuda.synchronize()
+        dt = torch.tensor([time.perf_counter() - t0], dtype=torch.float64, device=device)
+        barrier()
+        if world > 1:
+            dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        assert np.array_equal(h_out[:64], curves)
+        e2e = {"value": world * perms_n * args.steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": int(h_perms.nbytes) * world, "d2h_bytes_per_step": int(h_out.nbytes) * world,
+               "ms_per_step": float(dt.item()) / args.steps * 1e3,
+               "path": "pgx_pan_core_curves_host: pinned uint16 permutations in, int32 curves out, wall clock",
+               "host_rng_s_per_step_not_included": host_rng_s}
+        del h_out, h_out_owner
+    if sampler:
+        sampler.stop()
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    value = world * perms_n * args.steps / (ms_total / 1e3)
+    peak, peak_src = measured_peak()
+    a_perm = hp.algorithmic_bytes_per_perm
+    row_ms_per_launch = row_ms / max(1, calls)
+    achieved = a_perm * perms_n / (row_ms_per_launch / 1e3) / 1e9 if row_ms_per_launch > 0 else None
+    traffic = ncu_traffic(args.workload)
+    roofline = {
+        "bound": "hbm", "kernel": "minrank_kernel<8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
+        "algorithmic_bytes_per_perm": a_perm, "perms_per_launch": perms_n,
+        "ms_per_launch": row_ms_per_launch, "scan_ms_per_launch": scan_ms / max(1, calls),
+        "row_kernel_share_of_step": row_ms / ms_total if ms_total > 0 else None,
+        "streamed_bytes_per_row_pass": hp.streamed_bytes_per_pass,
+        "note": "algorithmic bytes = one pass over the canonical int32 gene-major CSR per permutation "
+                "(SURVEY.md 8d); the kernel streams folded uint16 rows once per 8 permutations, so "
+                "frac can exceed 1 -- see traffic and DESIGN.md",
+    }
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import build as oracle_build, cport
+        oracle_build.build()
+        threads = os.cpu_count() or 1
+        gm, sample_perms, t1 = cpu_sample(coo, n, args.cpu_seconds, threads)
+        t0 = time.perf_counter()
+        pan, core = cport.curves_direct(gm, sample_perms, n_threads=threads)
+        dt = time.perf_counter() - t0
+        # the CPU arm doubles as a checker of the GPU result on its sample
+        check = eng.curves_host(sample_perms[:threads].astype(np.uint16))
+        assert np.array_equal(check, np.hstack([pan, core])[:threads].astype(np.int32)), "GPU != oracle"
+        cpu = {"value": sample_perms.shape[0] / dt, "unit": UNIT, "cores": threads, "kind": "port",
+               "sample": "%d permutations of the same table (of %d), oracle C port of "
+                         "pangenome_analysis.py:81-90, %d threads" % (sample_perms.shape[0], perms_n, threads),
+               "single_thread_s_per_perm": t1}
+    config = workload_config(args.workload, coo, perms_n, world)
+    config["l2_policy"] = "inputs larger than L2: %.0f MB of permutations + %.0f MB of curves + %.0f MB of folded rows per step" % (
+        d_perms.numel() * 2 / 1e6, d_out.numel() * 4 / 1e6, hp.streamed_bytes_per_pass / 1e6)
+    config["gather"] = "NCCL gather of int32 curves to rank 0 inside the timed region" if world > 1 else "none (1 GPU)"
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+        "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": config,
+        "cells_per_s": value * n_genes * n, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+        "gpu_launches": int(launches), "clocks": clocks, "host_rng_s_for_perms": host_rng_s,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if world != args.gpus:
+        log("[bench] note: --gpus %d but WORLD_SIZE %d; using WORLD_SIZE" % (args.gpus, world))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+    else:
+        run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

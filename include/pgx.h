@@ -1,0 +1,131 @@
+/* pgx.h -- C ABI of libpgx_b200.so: the pan/core rarefaction + Bernoulli-grid hot path of
+ * pangenomix on NVIDIA B200 (sm_100a).
+ *
+ * The reference (AnnaLew/pangenomix) is pure Python and has no FFI of its own; the
+ * functions declared here are what a ctypes binding inside the reference's
+ * pangenome_analysis.py would call instead of its Python loops:
+ *
+ *   pgx_pan_core_curves[_host]   replaces the double loop of estimate_pan_core_size,
+ *                                /root/reference/pangenomix/pangenome_analysis.py:81-90
+ *   pgx_bernoulli_ll_grad        replaces __bernoulli_grid_loglikelihood__ (:244-249) and
+ *                                __bernoulli_grid_loglikelihood_gradient__ (:257-266) as
+ *                                called from the L-BFGS-B lambdas at :156-160
+ *   pgx_legacy_shuffles          replaces the np.arange + np.random.shuffle pair at :84-85
+ *                                (numpy legacy MT19937 stream, bit-exact)
+ *
+ * Conventions: every function returns 0 on success and a non-zero code otherwise;
+ * pgx_last_error() then returns a thread-local message.  No C++ types, exceptions or
+ * torch types cross this boundary.  Pointers prefixed d_ are DEVICE pointers owned by
+ * the caller (the library never frees caller memory); h_ are HOST pointers.  Functions
+ * taking a ``stream`` (a cudaStream_t passed as void*) are asynchronous on that stream;
+ * the *_host variants are synchronous and move the data themselves.
+ */
+#ifndef PGX_H_
+#define PGX_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PGX_VERSION 100
+
+enum {
+    PGX_OK = 0,
+    PGX_ERR_INVALID = 1,   /* bad argument (null pointer, size out of range, ...) */
+    PGX_ERR_CUDA = 2,      /* a CUDA runtime call or kernel launch failed */
+    PGX_ERR_UNSUPPORTED = 3
+};
+
+/* Device-resident plan of a BINARY gene x genome presence/absence table, built once per
+ * matrix by the host (pangenomix_b200/plan.py) from ``df_genes.data`` -- the same object
+ * estimate_pan_core_size reads at pangenome_analysis.py:74.  Rows are "folded": each
+ * general gene stores the SHORTER of its present-genome list and its absent-genome list
+ * as sorted uint16 genome indices in 16-byte chunks (8 indices, padded with the sentinel
+ * index n_genomes).  Genes that are empty, universal, present in exactly one genome or
+ * absent from exactly one genome never reach the row kernel: they are closed forms of the
+ * permutation and are folded into the per-genome weight vectors below. */
+typedef struct pgx_plan {
+    const uint16_t *d_chunks;    /* [n_chunks * 8] folded genome indices, 16-byte aligned */
+    const int32_t *d_row_ptr;    /* [n_rows + 1]   first chunk of every folded row */
+    const int32_t *d_tasks;      /* [n_tasks * 2]  {first_row, n_rows<<8 | log2(lanes)<<1 | absent_list} */
+    const int32_t *d_w_present;  /* [n_genomes]    #genes present ONLY in genome c */
+    const int32_t *d_w_absent;   /* [n_genomes]    #genes absent ONLY from genome c */
+    int64_t n_chunks;
+    int32_t n_genomes;           /* N  (1 <= N <= 65535) */
+    int32_t n_genes;             /* G  (all genes of the table, incl. closed-form ones) */
+    int32_t n_rows;              /* folded rows that go through the row kernel */
+    int32_t n_tasks;
+    int32_t n_empty;             /* genes present in no genome */
+    int32_t n_full;              /* genes present in every genome */
+    int32_t sum_w_present;
+    int32_t sum_w_absent;
+} pgx_plan;
+
+int pgx_version(void);
+const char *pgx_last_error(void);
+
+/* SM count, opt-in shared memory per block and L2 size of the current device. */
+int pgx_device_info(int32_t *sm_count, int32_t *smem_optin_bytes, int64_t *l2_bytes);
+
+/* Pan/core curves for n_perm genome orders (pangenome_analysis.py:81-90).
+ *   d_perms  : [n_perm][N] uint16, row i = shuffle_indices of iteration i (:84-85)
+ *   d_curves : [n_perm][2N] int32; columns 0..N-1 = pan_genomes[i,:], N..2N-1 =
+ *              core_genomes[i,:] (the np.hstack layout of :97).  Overwritten.
+ * Asynchronous on ``stream``. */
+int pgx_pan_core_curves(const pgx_plan *plan, const uint16_t *d_perms, int64_t n_perm,
+                        int32_t *d_curves, void *stream);
+
+/* Same, float64 output exactly as the reference's DataFrame values (:76-77, :97).
+ * d_hist is caller scratch of n_perm * 2N int32. */
+int pgx_pan_core_curves_f64(const pgx_plan *plan, const uint16_t *d_perms, int64_t n_perm,
+                            int32_t *d_hist, double *d_curves, void *stream);
+
+/* Host-buffer entry point: h_perms [n_perm][N] uint16 and h_curves [n_perm][2N]
+ * (int32 when out_f64 == 0, float64 otherwise) live in host memory (pinned memory makes
+ * the copies asynchronous).  The plan stays device-resident.  The call pipelines
+ * H2D -> kernels -> D2H over two internal streams in blocks of ``perms_per_block``
+ * permutations (0 = choose) and returns when h_curves is complete. */
+int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int64_t n_perm,
+                             void *h_curves, int32_t out_f64, int64_t perms_per_block);
+
+/* Launch-shape overrides for experiments (0 = heuristic): permutations per CTA
+ * (1, 2, 4 or 8) and row splits per permutation batch. */
+int pgx_set_tuning(int32_t perms_per_cta, int32_t row_splits, int32_t threads_per_cta);
+
+/* Per-kernel timing for roofline reports: while enabled, every pgx_pan_core_curves*
+ * call brackets its row kernel and its scan kernel with CUDA events on the caller's
+ * stream.  pgx_profile_read waits for them, returns the summed durations (ms) and the
+ * number of calls since the last read, and releases the events. */
+int pgx_profile_enable(int32_t on);
+int pgx_profile_read(double *minrank_ms, double *scan_ms, int64_t *calls);
+
+/* Number of kernels this library has launched since load (bench.py's gpu_launches). */
+int64_t pgx_launch_count(void);
+
+/* Bernoulli grid: log-likelihood and gradient at (P, Q) (pangenome_analysis.py:244-266).
+ *   d_xbits     : [G][words_per_row] uint32, bit (j & 31) of word (j >> 5) = X[i][j]
+ *   d_row_count : [G] int32  = X.sum(axis=1);   d_col_count : [N] int32 = X.sum(axis=0)
+ *   d_p [G], d_q [N] float64;  d_ll [1], d_grad [G + N] float64 (dL/dp then dL/dq)
+ *   d_scratch   : pgx_bernoulli_scratch_bytes(G, N) bytes
+ * Deterministic (fixed reduction order).  Asynchronous on ``stream``. */
+size_t pgx_bernoulli_scratch_bytes(int64_t n_genes, int64_t n_genomes);
+int pgx_bernoulli_ll_grad(const uint32_t *d_xbits, int64_t words_per_row, int64_t n_genes,
+                          int64_t n_genomes, const int32_t *d_row_count,
+                          const int32_t *d_col_count, const double *d_p, const double *d_q,
+                          double *d_ll, double *d_grad, void *d_scratch, void *stream);
+
+/* numpy legacy RandomState stream (host): ``count`` consecutive
+ * ``a = np.arange(n); np.random.shuffle(a)`` results as uint16 rows, continuing from the
+ * MT19937 state in ``mt_key`` (624 words) / ``mt_pos`` exactly as
+ * np.random.get_state() reports them; the advanced state is written back so the caller
+ * can np.random.set_state() it.  Requires n <= 65535. */
+int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n, int64_t count,
+                        uint16_t *h_perms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PGX_H_ */

@@ -1,0 +1,121 @@
+"""ctypes binding of libpgx_b200.so (the C ABI declared in include/pgx.h).
+
+There is no fallback: if the shared object is missing or a call fails, the caller gets an
+exception, never a CPU result.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libpgx_b200.so")
+
+# every symbol include/pgx.h declares (tests check the library exports all of them)
+EXPORTS = (
+    "pgx_version", "pgx_last_error", "pgx_device_info", "pgx_pan_core_curves",
+    "pgx_pan_core_curves_f64", "pgx_pan_core_curves_host", "pgx_set_tuning",
+    "pgx_launch_count", "pgx_bernoulli_scratch_bytes", "pgx_bernoulli_ll_grad",
+    "pgx_legacy_shuffles", "pgx_profile_enable", "pgx_profile_read",
+)
+
+
+class PgxError(RuntimeError):
+    """A libpgx_b200 call returned a non-zero status."""
+
+
+class PgxPlan(ctypes.Structure):
+    """Mirror of ``struct pgx_plan`` (include/pgx.h)."""
+    _fields_ = [
+        ("d_chunks", ctypes.c_void_p),
+        ("d_row_ptr", ctypes.c_void_p),
+        ("d_tasks", ctypes.c_void_p),
+        ("d_w_present", ctypes.c_void_p),
+        ("d_w_absent", ctypes.c_void_p),
+        ("n_chunks", ctypes.c_int64),
+        ("n_genomes", ctypes.c_int32),
+        ("n_genes", ctypes.c_int32),
+        ("n_rows", ctypes.c_int32),
+        ("n_tasks", ctypes.c_int32),
+        ("n_empty", ctypes.c_int32),
+        ("n_full", ctypes.c_int32),
+        ("sum_w_present", ctypes.c_int32),
+        ("sum_w_absent", ctypes.c_int32),
+    ]
+
+
+_lib = None
+
+
+def load():
+    """Loads the library once; raises if it has not been built (python -m pangenomix_b200.build)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise PgxError(
+            "%s is missing: build it with `python -m pangenomix_b200.build` "
+            "(there is no CPU fallback)" % LIB_PATH)
+    lib = ctypes.CDLL(LIB_PATH)
+    vp, i32, i64 = ctypes.c_void_p, ctypes.c_int32, ctypes.c_int64
+    plan_p = ctypes.POINTER(PgxPlan)
+    lib.pgx_version.restype = ctypes.c_int
+    lib.pgx_version.argtypes = []
+    lib.pgx_last_error.restype = ctypes.c_char_p
+    lib.pgx_last_error.argtypes = []
+    lib.pgx_device_info.restype = ctypes.c_int
+    lib.pgx_device_info.argtypes = [ctypes.POINTER(i32), ctypes.POINTER(i32), ctypes.POINTER(i64)]
+    lib.pgx_pan_core_curves.restype = ctypes.c_int
+    lib.pgx_pan_core_curves.argtypes = [plan_p, vp, i64, vp, vp]
+    lib.pgx_pan_core_curves_f64.restype = ctypes.c_int
+    lib.pgx_pan_core_curves_f64.argtypes = [plan_p, vp, i64, vp, vp, vp]
+    lib.pgx_pan_core_curves_host.restype = ctypes.c_int
+    lib.pgx_pan_core_curves_host.argtypes = [plan_p, vp, i64, vp, i32, i64]
+    lib.pgx_set_tuning.restype = ctypes.c_int
+    lib.pgx_set_tuning.argtypes = [i32, i32, i32]
+    lib.pgx_launch_count.restype = i64
+    lib.pgx_launch_count.argtypes = []
+    lib.pgx_bernoulli_scratch_bytes.restype = ctypes.c_size_t
+    lib.pgx_bernoulli_scratch_bytes.argtypes = [i64, i64]
+    lib.pgx_bernoulli_ll_grad.restype = ctypes.c_int
+    lib.pgx_bernoulli_ll_grad.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.pgx_legacy_shuffles.restype = ctypes.c_int
+    lib.pgx_legacy_shuffles.argtypes = [vp, ctypes.POINTER(i32), i64, i64, vp]
+    lib.pgx_profile_enable.restype = ctypes.c_int
+    lib.pgx_profile_enable.argtypes = [i32]
+    lib.pgx_profile_read.restype = ctypes.c_int
+    lib.pgx_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                     ctypes.POINTER(i64)]
+    _lib = lib
+    return lib
+
+
+def check(status):
+    if status != 0:
+        message = load().pgx_last_error().decode("utf-8", "replace")
+        raise PgxError("libpgx_b200 error %d: %s" % (status, message))
+
+
+def launch_count():
+    return int(load().pgx_launch_count())
+
+
+def profile_enable(on=True):
+    check(load().pgx_profile_enable(1 if on else 0))
+
+
+def profile_read():
+    """(row-kernel ms, scan-kernel ms, calls) accumulated since the last read."""
+    a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    check(load().pgx_profile_read(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
+    return a.value, b.value, c.value
+
+
+def set_tuning(perms_per_cta=0, row_splits=0, threads_per_cta=0):
+    check(load().pgx_set_tuning(int(perms_per_cta), int(row_splits), int(threads_per_cta)))
+
+
+def device_info():
+    sm, smem, l2 = ctypes.c_int32(), ctypes.c_int32(), ctypes.c_int64()
+    check(load().pgx_device_info(ctypes.byref(sm), ctypes.byref(smem), ctypes.byref(l2)))
+    return {"sm_count": sm.value, "smem_optin_bytes": smem.value, "l2_bytes": l2.value}

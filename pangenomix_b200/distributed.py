@@ -1,0 +1,121 @@
+"""Permutation sharding across the GPUs of one box.
+
+Genome orders are independent given the matrix, so the matrix is replicated, rank r
+rarefies the contiguous block [lo_r, hi_r) of the ``num_iter`` permutations, and one
+gather brings the small curve blocks together.  Contiguous blocks keep row ``Iter{i}``
+where the single-GPU path puts it.  One process per GPU, ``torch.distributed`` (NCCL over
+NVLink on the B200 box; gloo in the CPU tests of this host-side logic).
+
+The only RNG that matters is rank 0's global numpy stream -- rank 0 draws all
+``num_iter`` shuffles exactly as the reference does (pangenome_analysis.py:84-85) and
+broadcasts the table.
+"""
+from __future__ import annotations
+
+import numpy as np
+
+
+def shard_bounds(n_items, world_size, rank):
+    """Contiguous block of ``rank``: sizes differ by at most one, earlier ranks get the extra."""
+    base, extra = divmod(int(n_items), int(world_size))
+    lo = rank * base + min(rank, extra)
+    return lo, lo + base + (1 if rank < extra else 0)
+
+
+def _dist():
+    import torch.distributed as dist
+    return dist
+
+
+def sharded_curves(perms, n_genomes, compute, device=None, group=None, dst=None):
+    """Rarefies ``perms`` ([num_iter, N] uint16, significant on rank 0 only) across the group.
+
+    compute : callable(numpy uint16 [k, N]) -> numpy int32 [k, 2N] on this rank's GPU
+    dst     : None -> every rank returns the full table (all_gather);
+              r    -> only rank r returns it (gather), the others return None.
+    """
+    import torch
+    dist = _dist()
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    device = torch.device("cpu") if device is None else torch.device(device)
+
+    shape = torch.zeros(1, dtype=torch.int64, device=device)
+    if rank == 0:
+        perms = np.ascontiguousarray(perms, dtype=np.uint16)
+        if perms.ndim != 2 or perms.shape[1] != n_genomes:
+            raise ValueError("perms must have shape [num_iter, %d]" % n_genomes)
+        shape[0] = perms.shape[0]
+    dist.broadcast(shape, src=0, group=group)
+    num_iter = int(shape.item())
+
+    table = torch.empty((num_iter, n_genomes), dtype=torch.int16, device=device)
+    if rank == 0:
+        table.copy_(torch.from_numpy(perms.view(np.int16)))
+    if num_iter:
+        # neither gloo nor NCCL moves 16-bit integers: broadcast the bytes
+        dist.broadcast(table.view(torch.uint8), src=0, group=group)
+
+    lo, hi = shard_bounds(num_iter, world, rank)
+    mine = table[lo:hi].cpu().numpy().view(np.uint16)
+    local = compute(mine) if hi > lo else np.zeros((0, 2 * n_genomes), dtype=np.int32)
+    local = np.ascontiguousarray(local, dtype=np.int32)
+    if local.shape != (hi - lo, 2 * n_genomes):
+        raise ValueError("compute returned shape %s, expected %s" % (local.shape, (hi - lo, 2 * n_genomes)))
+
+    # equal-sized padded blocks so a single (all_)gather moves everything
+    width = shard_bounds(num_iter, world, 0)[1]
+    block = torch.zeros((max(width, 1), 2 * n_genomes), dtype=torch.int32, device=device)
+    if hi > lo:
+        block[:hi - lo].copy_(torch.from_numpy(local))
+    if dst is None:
+        gathered = torch.empty((world * block.shape[0], block.shape[1]), dtype=torch.int32, device=device)
+        dist.all_gather_into_tensor(gathered, block, group=group)
+        parts = gathered.view(world, block.shape[0], block.shape[1])
+    else:
+        parts = [torch.empty_like(block) for _ in range(world)] if rank == dst else None
+        dist.gather(block, gather_list=parts, dst=dst, group=group)
+        if rank != dst:
+            return None
+    out = np.empty((num_iter, 2 * n_genomes), dtype=np.int32)
+    for r in range(world):
+        r_lo, r_hi = shard_bounds(num_iter, world, r)
+        if r_hi > r_lo:
+            out[r_lo:r_hi] = parts[r][:r_hi - r_lo].cpu().numpy()
+    return out
+
+
+def estimate_pan_core_size_sharded(df_genes, num_iter, log_batch=-1, group=None, dst=None, compute=None):
+    """Multi-GPU ``estimate_pan_core_size``: same DataFrame as the single-GPU call on the
+    ranks that receive it (all ranks for ``dst=None``), None elsewhere.
+
+    Every rank must call it with the same table; only rank 0's numpy RNG is consumed.
+    ``compute`` is injectable for the CPU tests of the sharding logic; by default each rank
+    runs the CUDA engine on its own device.
+    """
+    import pandas as pd
+    import torch
+    from .engine import PanCoreEngine, draw_legacy_permutations
+    dist = _dist()
+    rank = dist.get_rank(group)
+    num_genes, num_strains = df_genes.shape
+    device = None
+    if compute is None:
+        engine = PanCoreEngine(df_genes.data)
+        device = engine.device
+        compute = engine.curves_host
+    perms = None
+    if rank == 0:
+        print('Converting DataFrame to matrix...')
+        print('Generating pan/core curves from shuffled strains')
+        if log_batch > 0:
+            for it in range(log_batch, num_iter + 1, log_batch):
+                print('\tIteration', it, 'of', num_iter)
+        perms = draw_legacy_permutations(num_strains, num_iter)
+    curves = sharded_curves(perms, num_strains, compute, device=device, group=group, dst=dst)
+    if curves is None:
+        return None
+    iter_index = ['Iter' + str(x) for x in range(1, num_iter + 1)]
+    pan_cols = ['Pan' + str(x) for x in range(1, num_strains + 1)]
+    core_cols = ['Core' + str(x) for x in range(1, num_strains + 1)]
+    return pd.DataFrame(index=iter_index, columns=pan_cols + core_cols,
+                        data=curves.astype(np.float64))

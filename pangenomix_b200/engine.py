@@ -1,0 +1,283 @@
+"""Device-side engines behind the drop-in API: PanCoreEngine (rarefaction) and BernoulliGrid.
+
+PyTorch is used for plumbing only -- device buffers, pinned host buffers, streams.  All
+arithmetic happens in libpgx_b200.so (hand-written sm_100a kernels, include/pgx.h).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+
+import numpy as np
+
+from . import _native
+from .plan import HostPlan, build_host_plan
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _require_cuda(device=None):
+    torch = _torch()
+    if not torch.cuda.is_available():
+        raise _native.PgxError(
+            "no CUDA device visible: pangenomix_b200 has no CPU fallback for the pan/core "
+            "and Bernoulli-grid kernels")
+    if device is None:
+        return torch.device("cuda", torch.cuda.current_device())
+    device = torch.device(device)
+    if device.type != "cuda":
+        raise _native.PgxError("device must be a CUDA device, got %s" % device)
+    if device.index is None:
+        device = torch.device("cuda", torch.cuda.current_device())
+    return device
+
+
+def _u16_view(t):
+    """torch has few uint16 ops; device buffers of uint16 data are carried as int16."""
+    return t
+
+
+def pinned_empty(shape, dtype):
+    """numpy array backed by page-locked memory (returns (array, owner tensor))."""
+    torch = _torch()
+    tdtype = {np.dtype(np.uint16): torch.int16, np.dtype(np.int32): torch.int32,
+              np.dtype(np.float64): torch.float64, np.dtype(np.int16): torch.int16}[np.dtype(dtype)]
+    owner = torch.empty(tuple(int(s) for s in shape), dtype=tdtype, pin_memory=True)
+    arr = owner.numpy()
+    if np.dtype(dtype) == np.uint16:
+        arr = arr.view(np.uint16)
+    return arr, owner
+
+
+def draw_legacy_permutations(n, count, out=None):
+    """``count`` x (np.arange(n); np.random.shuffle) from the GLOBAL legacy numpy stream.
+
+    Consumes exactly what /root/reference/pangenomix/pangenome_analysis.py:84-85 consumes,
+    so the global RNG state after the call equals the reference's.  The stream is advanced
+    by libpgx's bit-exact MT19937 restatement (pgx_legacy_shuffles) through
+    np.random.get_state()/set_state(); set PGX_NUMPY_SHUFFLE=1 to call numpy itself.
+    """
+    n, count = int(n), int(count)
+    if out is None:
+        out = np.empty((count, n), dtype=np.uint16)
+    if out.shape != (count, n) or out.dtype != np.uint16 or not out.flags.c_contiguous:
+        raise ValueError("out must be a C-contiguous uint16 array of shape (count, n)")
+    if n > 65535:
+        raise ValueError("n_genomes = %d exceeds 65535" % n)
+    state = np.random.get_state()
+    if os.environ.get("PGX_NUMPY_SHUFFLE") == "1" or state[0] != "MT19937":
+        for i in range(count):
+            a = np.arange(n)
+            np.random.shuffle(a)
+            out[i] = a
+        return out
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int32(int(state[2]))
+    _native.check(_native.load().pgx_legacy_shuffles(
+        key.ctypes.data, ctypes.byref(pos), n, count, out.ctypes.data))
+    np.random.set_state((state[0], key, int(pos.value), state[3], state[4]))
+    return out
+
+
+class PanCoreEngine:
+    """A presence/absence table resident on one GPU, ready to be rarefied.
+
+    ``data`` is ``df_genes.data`` (scipy COO gene x genome, pangenome_analysis.py:74).
+    """
+
+    def __init__(self, data, device=None, host_plan: HostPlan | None = None):
+        torch = _torch()
+        self.device = _require_cuda(device)
+        self.lib = _native.load()
+        self.host_plan = host_plan if host_plan is not None else build_host_plan(data)
+        hp = self.host_plan
+        self.n_genes, self.n_genomes = hp.n_genes, hp.n_genomes
+
+        def up(arr, as_dtype):
+            t = torch.from_numpy(np.ascontiguousarray(arr).view(as_dtype).reshape(-1))
+            return t.to(self.device)
+
+        self._chunks = up(hp.chunks, np.int16)
+        self._row_ptr = up(hp.row_ptr, np.int32)
+        self._tasks = up(hp.tasks, np.int32)
+        self._w_present = up(hp.w_present, np.int32)
+        self._w_absent = up(hp.w_absent, np.int32)
+        self.c_plan = _native.PgxPlan(
+            d_chunks=self._chunks.data_ptr() if hp.n_chunks else None,
+            d_row_ptr=self._row_ptr.data_ptr(),
+            d_tasks=self._tasks.data_ptr() if hp.n_tasks else None,
+            d_w_present=self._w_present.data_ptr(),
+            d_w_absent=self._w_absent.data_ptr(),
+            n_chunks=hp.n_chunks, n_genomes=hp.n_genomes, n_genes=hp.n_genes,
+            n_rows=hp.n_rows, n_tasks=hp.n_tasks, n_empty=hp.n_empty, n_full=hp.n_full,
+            sum_w_present=int(hp.w_present.sum()), sum_w_absent=int(hp.w_absent.sum()))
+
+    # ---- device-resident path -------------------------------------------------------
+    def curves_device(self, perms, out=None):
+        """perms: CUDA int16/uint16 tensor [n_perm, N] (uint16 bit patterns) -> int32 [n_perm, 2N].
+
+        Asynchronous on the current torch stream.
+        """
+        torch = _torch()
+        if perms.device != self.device or perms.dim() != 2 or perms.shape[1] != self.n_genomes:
+            raise ValueError("perms must be a [n_perm, %d] tensor on %s" % (self.n_genomes, self.device))
+        if perms.element_size() != 2 or not perms.is_contiguous():
+            raise ValueError("perms must be contiguous 16-bit integers")
+        n_perm = int(perms.shape[0])
+        if out is None:
+            out = torch.empty((n_perm, 2 * self.n_genomes), dtype=torch.int32, device=self.device)
+        elif out.shape != (n_perm, 2 * self.n_genomes) or out.dtype != torch.int32 or \
+                not out.is_contiguous() or out.device != self.device:
+            raise ValueError("out must be a contiguous int32 [n_perm, 2N] tensor on the engine's device")
+        with torch.cuda.device(self.device):
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _native.check(self.lib.pgx_pan_core_curves(
+                ctypes.byref(self.c_plan), perms.data_ptr(), n_perm, out.data_ptr(), stream))
+        return out
+
+    # ---- host-buffer path (the C ABI moves the data) ----------------------------------
+    def curves_host(self, perms, out=None, out_f64=False, perms_per_block=0):
+        """perms: numpy uint16 [n_perm, N] in host memory -> numpy [n_perm, 2N] (int32 or float64)."""
+        torch = _torch()
+        perms = np.ascontiguousarray(perms)
+        if perms.dtype != np.uint16:
+            if perms.size and (perms.min() < 0 or perms.max() >= self.n_genomes):
+                raise ValueError("permutation entries out of range")
+            perms = perms.astype(np.uint16)
+        if perms.ndim != 2 or perms.shape[1] != self.n_genomes:
+            raise ValueError("perms must have shape [n_perm, %d]" % self.n_genomes)
+        n_perm = perms.shape[0]
+        want = np.float64 if out_f64 else np.int32
+        if out is None:
+            out = np.empty((n_perm, 2 * self.n_genomes), dtype=want)
+        if out.shape != (n_perm, 2 * self.n_genomes) or out.dtype != want or not out.flags.c_contiguous:
+            raise ValueError("out has the wrong shape / dtype")
+        with torch.cuda.device(self.device):
+            _native.check(self.lib.pgx_pan_core_curves_host(
+                ctypes.byref(self.c_plan), perms.ctypes.data, n_perm, out.ctypes.data,
+                1 if out_f64 else 0, int(perms_per_block)))
+        return out
+
+    # ---- the reference's call: draw from np.random, return float64 (num_iter, 2N) -----
+    def estimate(self, num_iter, log_batch=-1, block=None):
+        """pangenome_analysis.py:76-90: curves for ``num_iter`` shuffles of the global RNG.
+
+        Host shuffles of block k+1 overlap the H2D copy, kernels and D2H copy of block k.
+        """
+        torch = _torch()
+        num_iter = int(num_iter)
+        n = self.n_genomes
+        out, out_owner = pinned_empty((num_iter, 2 * n), np.float64)
+        if num_iter == 0:
+            return out
+        if block is None:
+            block = max(32, min(4096, (32 << 20) // (16 * n)))
+        block = max(1, min(int(block), num_iter))
+        out_t = out_owner
+        with torch.cuda.device(self.device):
+            streams = [torch.cuda.Stream(self.device) for _ in range(2)]
+            stage = [pinned_empty((block, n), np.uint16) for _ in range(2)]
+            d_perm = [torch.empty((block, n), dtype=torch.int16, device=self.device) for _ in range(2)]
+            d_hist = [torch.empty((block, 2 * n), dtype=torch.int32, device=self.device) for _ in range(2)]
+            d_out = [torch.empty((block, 2 * n), dtype=torch.float64, device=self.device) for _ in range(2)]
+            done = [None, None]
+            slot = 0
+            for p0 in range(0, num_iter, block):
+                cnt = min(block, num_iter - p0)
+                if log_batch > 0:
+                    first = ((p0 + log_batch) // log_batch) * log_batch
+                    for it in range(first, p0 + cnt + 1, log_batch):
+                        print('\tIteration', it, 'of', num_iter)       # :82-83
+                if done[slot] is not None:
+                    done[slot].synchronize()         # staging buffer free again
+                host_perm, host_owner = stage[slot]
+                draw_legacy_permutations(n, cnt, out=host_perm[:cnt])
+                with torch.cuda.stream(streams[slot]):
+                    d_perm[slot][:cnt].copy_(host_owner[:cnt], non_blocking=True)
+                    _native.check(self.lib.pgx_pan_core_curves_f64(
+                        ctypes.byref(self.c_plan), d_perm[slot].data_ptr(), cnt,
+                        d_hist[slot].data_ptr(), d_out[slot].data_ptr(),
+                        streams[slot].cuda_stream))
+                    out_t[p0:p0 + cnt].copy_(d_out[slot][:cnt], non_blocking=True)
+                    ev = torch.cuda.Event()
+                    ev.record(streams[slot])
+                    done[slot] = ev
+                slot ^= 1
+            for s in streams:
+                s.synchronize()
+        return out
+
+
+class BernoulliGrid:
+    """Dense 0/1 gene x genome table, bit-packed on the GPU, for LL / gradient evaluations
+    (pangenome_analysis.py:244-266)."""
+
+    def __init__(self, x, device=None):
+        torch = _torch()
+        self.device = _require_cuda(device)
+        self.lib = _native.load()
+        x = np.asarray(x)
+        if x.ndim != 2 or x.shape[0] < 1 or x.shape[1] < 1:
+            raise ValueError("expected a non-empty 2-D gene x genome table")
+        xb = x != 0
+        if not np.array_equal(xb, x):
+            raise ValueError("compute_bernoulli_grid_core_genome needs a dense BINARY (0/1) table "
+                             "(pangenome_analysis.py:114-115)")
+        self.n_genes, self.n_genomes = x.shape
+        packed = np.packbits(xb, axis=1, bitorder="little")
+        words = (self.n_genomes + 31) // 32
+        padded = np.zeros((self.n_genes, words * 4), dtype=np.uint8)
+        padded[:, :packed.shape[1]] = packed
+        self.words_per_row = words
+        self.row_count = xb.sum(axis=1).astype(np.int32)
+        self.col_count = xb.sum(axis=0).astype(np.int32)
+        dev = self.device
+        self._xbits = torch.from_numpy(padded.view(np.int32).reshape(-1)).to(dev)
+        self._row_count = torch.from_numpy(self.row_count).to(dev)
+        self._col_count = torch.from_numpy(self.col_count).to(dev)
+        total = self.n_genes + self.n_genomes
+        self._pq = torch.empty(total, dtype=torch.float64, device=dev)
+        self._res = torch.empty(total + 1, dtype=torch.float64, device=dev)   # [ll, grad...]
+        scratch = int(self.lib.pgx_bernoulli_scratch_bytes(self.n_genes, self.n_genomes))
+        if scratch == 0:
+            raise _native.PgxError("Bernoulli grid shape %s x %s is not supported" % x.shape)
+        self._scratch = torch.empty((scratch + 7) // 8, dtype=torch.float64, device=dev)
+        self._h_pq = torch.empty(total, dtype=torch.float64, pin_memory=True)
+        self._h_res = torch.empty(total + 1, dtype=torch.float64, pin_memory=True)
+        self._last_x = None
+        self.evaluations = 0
+
+    def ll_grad(self, pq):
+        """(log-likelihood, gradient[G+N]) at PQ = concat(P, Q); one launch pair, cached by value."""
+        torch = _torch()
+        pq = np.ascontiguousarray(pq, dtype=np.float64)
+        if pq.shape != (self.n_genes + self.n_genomes,):
+            raise ValueError("PQ must have length n_genes + n_genomes")
+        if self._last_x is not None and np.array_equal(pq, self._last_x):
+            return self._last
+        g = self.n_genes
+        with torch.cuda.device(self.device):
+            self._h_pq.numpy()[:] = pq
+            self._pq.copy_(self._h_pq, non_blocking=True)
+            stream = torch.cuda.current_stream(self.device).cuda_stream
+            _native.check(self.lib.pgx_bernoulli_ll_grad(
+                self._xbits.data_ptr(), self.words_per_row, self.n_genes, self.n_genomes,
+                self._row_count.data_ptr(), self._col_count.data_ptr(),
+                self._pq.data_ptr(), self._pq.data_ptr() + 8 * g,
+                self._res.data_ptr(), self._res.data_ptr() + 8, self._scratch.data_ptr(), stream))
+            self._h_res.copy_(self._res, non_blocking=True)
+            torch.cuda.current_stream(self.device).synchronize()
+        res = self._h_res.numpy()
+        self._last_x = pq.copy()
+        self._last = (float(res[0]), res[1:].copy())
+        self.evaluations += 1
+        return self._last
+
+    def loglikelihood(self, p, q):
+        return self.ll_grad(np.concatenate((p, q)))[0]
+
+    def gradient(self, p, q):
+        return self.ll_grad(np.concatenate((p, q)))[1]

@@ -1,0 +1,79 @@
+"""CPU-side checks of the C-ABI library: it loads, exports everything include/pgx.h
+declares, reports errors through pgx_last_error, and its host-only entry point
+(pgx_legacy_shuffles) reproduces numpy's legacy stream.  No kernels are launched here."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from conftest import REPO, draw_perms
+from pangenomix_b200 import _native, engine
+
+
+def test_library_exports_every_declared_symbol():
+    header = open(os.path.join(REPO, "include", "pgx.h")).read()
+    declared = set(re.findall(r"\b(pgx_[a-z0-9_]+)\s*\(", header))
+    declared -= {"pgx_plan"}
+    assert declared == set(_native.EXPORTS)
+    lib = _native.load()
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.pgx_version() == 100
+
+
+def test_plan_struct_layout_matches_header():
+    # 5 pointers + int64 + 8 int32 = 80 bytes, no padding surprises
+    assert ctypes.sizeof(_native.PgxPlan) == 5 * 8 + 8 + 8 * 4
+
+
+def test_invalid_arguments_set_last_error():
+    lib = _native.load()
+    rc = lib.pgx_pan_core_curves(None, None, 1, None, None)
+    assert rc == 1
+    assert b"plan is null" in lib.pgx_last_error()
+    plan = _native.PgxPlan(n_genomes=70000)
+    rc = lib.pgx_pan_core_curves(ctypes.byref(plan), None, 1, None, None)
+    assert rc == 3 and b"65535" in lib.pgx_last_error()
+    with pytest.raises(_native.PgxError):
+        _native.check(rc)
+    assert lib.pgx_bernoulli_scratch_bytes(0, 5) == 0
+    assert lib.pgx_bernoulli_scratch_bytes(4000, 400) >= 8 * (4000 + 400)
+
+
+@pytest.mark.parametrize("n", [1, 2, 3, 5, 50, 255, 256, 257, 400, 4096, 10000, 65535])
+def test_legacy_shuffles_are_numpys(n):
+    count = 4 if n < 20000 else 2
+    np.random.seed(12345)
+    got = engine.draw_legacy_permutations(n, count)
+    state_after = np.random.get_state()
+    want = draw_perms(12345, n, count)
+    assert np.array_equal(got, want)
+    ref_state = np.random.get_state()
+    assert np.array_equal(state_after[1], ref_state[1]) and state_after[2] == ref_state[2]
+    # and the stream continues identically
+    np.random.set_state(state_after)
+    a = np.random.random_sample(3)
+    np.random.set_state(ref_state)
+    assert np.array_equal(a, np.random.random_sample(3))
+
+
+def test_legacy_shuffles_mid_block_state_and_numpy_mode(monkeypatch):
+    np.random.seed(99)
+    np.random.random_sample(123)           # leave the generator mid-block
+    state = np.random.get_state()
+    got = engine.draw_legacy_permutations(37, 5)
+    np.random.set_state(state)
+    monkeypatch.setenv("PGX_NUMPY_SHUFFLE", "1")
+    assert np.array_equal(engine.draw_legacy_permutations(37, 5), got)
+
+
+def test_no_cuda_means_loud_failure(have_cuda):
+    if have_cuda:
+        pytest.skip("CUDA present")
+    import scipy.sparse
+    with pytest.raises(_native.PgxError):
+        engine.PanCoreEngine(scipy.sparse.coo_matrix(np.eye(4, dtype=np.int64)))
+    with pytest.raises(_native.PgxError):
+        engine.BernoulliGrid(np.eye(4))

@@ -1,0 +1,230 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle and the reference-generated
+golden fixtures.  Bit-exact for the curves; fp64 likelihoods within 1e-9 relative (the
+tolerance BASELINE.json's north_star states)."""
+import numpy as np
+import pandas as pd
+import pytest
+import scipy.sparse
+
+import oracle
+from conftest import CURVE_CASES, draw_perms, golden_matrix, load_golden
+
+pytestmark = pytest.mark.gpu
+
+LL_RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def engine_mod():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from pangenomix_b200 import _native, engine
+    _native.load()
+    yield engine
+    _native.set_tuning(0, 0, 0)
+
+
+def _oracle_curves(coo, perms):
+    pan, core = oracle.pan_core_curves_minrank(coo, np.asarray(perms, dtype=np.int64))
+    return np.hstack([pan, core]).astype(np.int32)
+
+
+@pytest.mark.parametrize("name", CURVE_CASES)
+def test_curves_match_reference_fixtures(engine_mod, name):
+    import torch
+    g = load_golden(name)
+    coo = golden_matrix(name, g)
+    eng = engine_mod.PanCoreEngine(coo)
+    perms = draw_perms(int(g["seed"]), coo.shape[1], int(g["num_iter"])).astype(np.uint16)
+    want = g["curves"]
+    got_host = eng.curves_host(perms)
+    assert got_host.dtype == np.int32 and np.array_equal(got_host, want)
+    got_f64 = eng.curves_host(perms, out_f64=True, perms_per_block=3)
+    assert got_f64.dtype == np.float64 and np.array_equal(got_f64, want.astype(np.float64))
+    d_perms = torch.from_numpy(perms.view(np.int16)).cuda()
+    got_dev = eng.curves_device(d_perms).cpu().numpy()
+    assert np.array_equal(got_dev, want)
+
+
+@pytest.mark.parametrize("name", ["kat_6x5", "synth_800x50_s0", "c1_8000x50", "c2slice_4000x400"])
+def test_drop_in_api_frame_rng_and_heaps(engine_mod, name, capsys):
+    from pangenomix_b200 import pangenome_analysis as pa, plot, sparse_utils as su, synth
+    g = load_golden(name)
+    coo = golden_matrix(name, g)
+    index, columns = synth.labels_for(*coo.shape)
+    lsdf = su.LightSparseDataFrame(index, columns, coo)
+    num_iter, n = int(g["num_iter"]), coo.shape[1]
+    np.random.seed(int(g["seed"]))
+    df = pa.estimate_pan_core_size(lsdf, num_iter, log_batch=max(1, num_iter // 2))
+    follow = np.random.random_sample(2)
+    out = capsys.readouterr().out
+    assert out.startswith("Converting DataFrame to matrix...\nGenerating pan/core curves from shuffled strains\n")
+    assert "\tIteration %d of %d" % (max(1, num_iter // 2), num_iter) in out
+    assert isinstance(df, pd.DataFrame) and df.values.dtype == np.float64
+    assert df.shape == (num_iter, 2 * n)
+    assert list(df.index) == ["Iter%d" % (i + 1) for i in range(num_iter)]
+    assert list(df.columns) == ["Pan%d" % (i + 1) for i in range(n)] + ["Core%d" % (i + 1) for i in range(n)]
+    assert np.array_equal(df.values, g["curves"].astype(np.float64))
+    # exactly num_iter shuffles were consumed from the global stream
+    draw_perms(int(g["seed"]), n, num_iter)
+    assert np.array_equal(follow, np.random.random_sample(2))
+    mean = plot.calculate_mean(df)
+    assert np.array_equal(mean.values[0], g["mean"])
+    fit = pa.fit_heaps_by_iteration(mean)
+    np.testing.assert_allclose(fit.values[0], g["heaps_mean"], rtol=1e-12)
+    fit_it = pa.fit_heaps_by_iteration(df.iloc[:min(num_iter, 8)])
+    np.testing.assert_allclose(fit_it.values, g["heaps_iter"], rtol=1e-12)
+    assert list(fit_it.columns) == ["alpha", "kappa"] and fit_it.index[0] == "Iter1"
+
+
+def _mixed_matrix(n, seed=5, per_class=24):
+    rng = np.random.RandomState(seed)
+    dens = np.concatenate([np.full(per_class, d) for d in
+                           (0.0, 2.0 / n, 0.004, 0.015, 0.03, 0.06, 0.12, 0.3, 0.5, 0.8, 0.97, 1.0 - 2.0 / n, 1.0)])
+    x = (rng.random_sample((dens.size, n)) < dens[:, None]).astype(np.int64)
+    return scipy.sparse.coo_matrix(x)
+
+
+@pytest.mark.parametrize("perms_per_cta", [1, 2, 4, 8])
+@pytest.mark.parametrize("splits,threads", [(1, 64), (3, 256), (7, 1024)])
+def test_every_launch_shape_and_lane_class(engine_mod, perms_per_cta, splits, threads):
+    from pangenomix_b200 import _native
+    coo = _mixed_matrix(700)
+    eng = engine_mod.PanCoreEngine(coo)
+    lanes = sorted({(int(m) >> 1) & 7 for m in eng.host_plan.tasks[:, 1]})
+    assert lanes == [0, 1, 2, 3, 4, 5]
+    perms = draw_perms(3, 700, 13).astype(np.uint16)       # 13: not a multiple of any batch
+    want = _oracle_curves(coo, perms)
+    _native.set_tuning(perms_per_cta, splits, threads)
+    try:
+        assert np.array_equal(eng.curves_host(perms), want)
+    finally:
+        _native.set_tuning(0, 0, 0)
+
+
+@pytest.mark.parametrize("n", [14000, 20000, 40000, 65535])
+def test_wide_tables_fall_back_to_smaller_batches(engine_mod, n):
+    """N above ~14.5k no longer fits 8 rank tables in shared memory: 4, 2, then 1 per CTA."""
+    coo = _mixed_matrix(n, seed=n, per_class=6)
+    eng = engine_mod.PanCoreEngine(coo)
+    perms = draw_perms(11, n, 5).astype(np.uint16)
+    assert np.array_equal(eng.curves_host(perms), _oracle_curves(coo, perms))
+
+
+def test_degenerate_shapes(engine_mod):
+    import torch
+    # no folded rows at all: everything is a closed form
+    x = np.zeros((6, 3), dtype=np.int64)
+    x[0] = 1
+    x[1, 2] = 1
+    x[2, :2] = 1
+    eng = engine_mod.PanCoreEngine(scipy.sparse.coo_matrix(x))
+    assert eng.host_plan.n_tasks == 0
+    perms = draw_perms(1, 3, 9).astype(np.uint16)
+    assert np.array_equal(eng.curves_host(perms), _oracle_curves(scipy.sparse.coo_matrix(x), perms))
+    # zero permutations, one permutation
+    assert eng.curves_host(perms[:0]).shape == (0, 6)
+    assert np.array_equal(eng.curves_host(perms[:1]), _oracle_curves(scipy.sparse.coo_matrix(x), perms[:1]))
+    # a single genome
+    one = scipy.sparse.coo_matrix(np.array([[1], [0], [1]], dtype=np.int64))
+    e1 = engine_mod.PanCoreEngine(one)
+    assert np.array_equal(e1.curves_host(np.zeros((4, 1), dtype=np.uint16)),
+                          np.tile(np.array([[2, 2]], dtype=np.int32), (4, 1)))
+    with pytest.raises(ValueError):
+        eng.curves_device(torch.zeros((2, 5), dtype=torch.int16, device="cuda"))
+
+
+def test_c2_full_size_properties_and_spot_parity(engine_mod):
+    """Config C2 (40,000 x 400, 1,000 permutations): size-independent invariants on every
+    curve, oracle parity on a sample of them."""
+    from pangenomix_b200 import synth
+    coo = synth.config_matrix("c2")
+    eng = engine_mod.PanCoreEngine(coo)
+    n, g = 400, 40000
+    np.random.seed(12345)
+    perms = engine_mod.draw_legacy_permutations(n, 1000)
+    curves = eng.curves_host(perms)
+    pan, core = curves[:, :n], curves[:, n:]
+    counts = np.diff(coo.tocsr().indptr)
+    assert np.all(np.diff(pan, axis=1) >= 0) and np.all(np.diff(core, axis=1) <= 0)
+    assert np.array_equal(pan[:, 0], core[:, 0])
+    assert np.all(pan[:, -1] == np.count_nonzero(counts)) and np.all(core[:, -1] == np.count_nonzero(counts == n))
+    col_sums = np.asarray(coo.sum(axis=0)).ravel()
+    assert np.array_equal(pan[:, 0], col_sums[perms[:, 0]])
+    sample = [0, 1, 499, 999]
+    assert np.array_equal(curves[sample], _oracle_curves(coo, perms[sample]))
+    # determinism and independence from the batch a permutation lands in
+    again = eng.curves_host(perms[::-1].copy())[::-1]
+    assert np.array_equal(again, curves)
+
+
+def test_c4_shape_sample(engine_mod):
+    """A 10,000-genome table (the C4 genome count, 1/10 of its genes so that the oracle
+    stays in seconds): 8 rank tables of 20 KB per CTA, long rows, every closed form."""
+    from pangenomix_b200 import synth
+    coo = synth.bernoulli_matrix(20000, 10000, 4500, seed=20244)
+    eng = engine_mod.PanCoreEngine(coo)
+    np.random.seed(12345)
+    perms = engine_mod.draw_legacy_permutations(10000, 24)
+    curves = eng.curves_host(perms)
+    assert np.array_equal(curves[[0, 7, 8, 23]], _oracle_curves(coo, perms[[0, 7, 8, 23]]))
+    pan, core = curves[:, :10000], curves[:, 10000:]
+    assert np.all(np.diff(pan, axis=1) >= 0) and np.all(np.diff(core, axis=1) <= 0)
+    assert np.array_equal(pan[:, 0], core[:, 0])
+
+
+# ---------------------------------------------------------------------------------------
+# Bernoulli grid
+# ---------------------------------------------------------------------------------------
+def test_bernoulli_ll_grad_fixtures(engine_mod):
+    g = load_golden("bernoulli_300x40")
+    grid = engine_mod.BernoulliGrid(g["x"].astype(np.float64))
+    for tag in ("0", "1"):
+        ll, grad = grid.ll_grad(np.concatenate((g["p" + tag], g["q" + tag])))
+        np.testing.assert_allclose(ll, g["ll" + tag], rtol=LL_RTOL)
+        np.testing.assert_allclose(grad, g["grad" + tag], rtol=LL_RTOL, atol=1e-9 * np.abs(g["grad" + tag]).max())
+    kat = engine_mod.BernoulliGrid(g["kat_x"])
+    ll, grad = kat.ll_grad(np.concatenate((g["kat_p"], g["kat_q"])))
+    np.testing.assert_allclose(ll, -2.502512292672613, rtol=LL_RTOL)
+    np.testing.assert_allclose(grad, g["kat_grad"], rtol=LL_RTOL)
+    with pytest.raises(ValueError):
+        engine_mod.BernoulliGrid(np.array([[0.0, 2.0]]))
+
+
+@pytest.mark.parametrize("shape", [(1, 1), (3, 33), (257, 513), (1000, 1300), (4000, 400)])
+def test_bernoulli_ll_grad_vs_oracle(engine_mod, shape):
+    from pangenomix_b200 import synth
+    x, _, _ = synth.bernoulli_grid_matrix(shape[0], shape[1], seed=shape[0] + shape[1])
+    rng = np.random.RandomState(1)
+    p = rng.uniform(0.8, 0.99999999, size=shape[0])
+    q = rng.uniform(0.8, 0.99999999, size=shape[1])
+    grid = engine_mod.BernoulliGrid(x)
+    ll, grad = grid.ll_grad(np.concatenate((p, q)))
+    want_ll, want_grad = oracle.bernoulli_ll(x, p, q), oracle.bernoulli_grad(x, p, q)
+    np.testing.assert_allclose(ll, want_ll, rtol=LL_RTOL)
+    np.testing.assert_allclose(grad, want_grad, rtol=LL_RTOL, atol=1e-9 * np.abs(want_grad).max())
+    ll2, grad2 = engine_mod.BernoulliGrid(x).ll_grad(np.concatenate((p, q)))
+    assert ll2 == ll and np.array_equal(grad2, grad)         # bit-reproducible
+
+
+def test_bernoulli_full_fit_matches_reference(engine_mod, capsys):
+    from pangenomix_b200 import pangenome_analysis as pa, synth
+    g = load_golden("bernoulli_300x40")
+    x = g["x"].astype(np.float64)
+    index, columns = synth.labels_for(*x.shape)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        df_opt, res = pa.compute_bernoulli_grid_core_genome(pd.DataFrame(x, index=index, columns=columns))
+    out = capsys.readouterr().out
+    assert "Initial loglikelihood:" in out and "Final loglikelihood:" in out
+    assert list(df_opt.columns) == ["initial", "optimum"]
+    assert list(df_opt.index) == ["Loglikelihood"] + ["p_" + s for s in index] + ["q_" + s for s in columns]
+    np.testing.assert_allclose(df_opt["initial"].values, g["fit_initial"], rtol=LL_RTOL)
+    # the optimiser path is sensitive to the last bits of LL/grad:
+    # compare the optimum itself and the core-gene call set it implies
+    np.testing.assert_allclose(-res.fun, -float(g["fit_fun"]), rtol=1e-7)
+    np.testing.assert_allclose(res.x, g["fit_x"], atol=2e-4)
+    ref_p, got_p = g["fit_x"][:300], res.x[:300]
+    margin = np.abs(ref_p - 0.99) > 1e-3
+    assert np.array_equal((got_p >= 0.99)[margin], (ref_p >= 0.99)[margin])

@@ -1,0 +1,57 @@
+"""Host planning (pangenomix_b200/plan.py) checked on the CPU against the golden curves by
+walking the plan exactly as the kernels do (tests/plan_emulator.py)."""
+import numpy as np
+import pytest
+import scipy.sparse
+
+from conftest import CURVE_CASES, draw_perms, golden_matrix, load_golden
+from pangenomix_b200.plan import build_host_plan
+from plan_emulator import curves_from_plan
+
+
+@pytest.mark.parametrize("name", CURVE_CASES)
+def test_plan_walk_matches_reference(name):
+    g = load_golden(name)
+    coo = golden_matrix(name, g)
+    hp = build_host_plan(coo)
+    iters = min(int(g["num_iter"]), 3 if coo.shape[0] > 2000 else 20)
+    perms = draw_perms(int(g["seed"]), coo.shape[1], iters)
+    got = curves_from_plan(hp, perms)
+    assert np.array_equal(got, g["curves"][:iters].astype(np.int64))
+
+
+def test_plan_accounts_for_every_gene():
+    g = load_golden("edge_500x37")
+    coo = golden_matrix("edge_500x37", g)
+    hp = build_host_plan(coo)
+    assert hp.n_empty >= 10 and hp.n_full >= 10
+    assert hp.w_present.sum() >= 20 and hp.w_absent.sum() >= 20
+    assert hp.n_rows + hp.n_empty + hp.n_full + hp.w_present.sum() + hp.w_absent.sum() == 500
+    assert hp.chunks.shape[0] % 8 == 0 and hp.chunks.dtype == np.uint16
+    assert hp.algorithmic_bytes_per_perm == 4 * coo.nnz + 4 * 501
+    assert np.all(hp.row_len <= 37 // 2)
+
+
+def test_plan_rejects_non_binary_and_oversize():
+    dup = scipy.sparse.coo_matrix((np.ones(3), ([0, 0, 1], [1, 1, 0])), shape=(2, 3))
+    with pytest.raises(ValueError):
+        build_host_plan(dup)
+    with pytest.raises(ValueError):
+        build_host_plan(scipy.sparse.coo_matrix((1, 70000)))
+    # explicit zeros are tolerated (they are absences)
+    z = scipy.sparse.coo_matrix((np.array([1, 0, 1]), ([0, 0, 1], [0, 1, 2])), shape=(2, 3))
+    assert build_host_plan(z).nnz == 2
+
+
+def test_plan_long_rows_and_all_lane_classes():
+    rng = np.random.RandomState(5)
+    n = 700
+    dens = np.concatenate([np.full(40, d) for d in (0.004, 0.015, 0.03, 0.06, 0.12, 0.3, 0.5, 0.8, 0.97)])
+    x = (rng.random_sample((dens.size, n)) < dens[:, None]).astype(np.int64)
+    hp = build_host_plan(scipy.sparse.coo_matrix(x))
+    lanes = sorted({(int(m) >> 1) & 7 for m in hp.tasks[:, 1]})
+    assert lanes == [0, 1, 2, 3, 4, 5]
+    perms = draw_perms(3, n, 4)
+    import oracle
+    pan, core = oracle.pan_core_curves_minrank(scipy.sparse.coo_matrix(x), perms)
+    assert np.array_equal(curves_from_plan(hp, perms), np.hstack([pan, core]).astype(np.int64))
