@@ -208,12 +208,14 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload):
-    """DRAM bytes per row-kernel launch from the committed ncu capture, if there is one."""
+def ncu_traffic(workload, kind, perms):
+    """DRAM bytes per launch of the dominant row kernel, scaled from the committed ncu capture
+    (profiles/roofline_traffic.json holds dram bytes per permutation), if there is one."""
     try:
         with open(os.path.join(REPO, "profiles", "roofline_traffic.json")) as f:
-            return json.load(f).get(workload)
-    except (OSError, ValueError):
+            per_perm = json.load(f)[workload][kind]["dram_bytes_per_perm"]
+        return float(per_perm) * perms
+    except (OSError, ValueError, KeyError, TypeError):
         return None
 
 
@@ -246,8 +248,8 @@ def run_b200(args, rank, world, local_rank):
     t = time.time()
     eng = engine.PanCoreEngine(coo, device=device)
     hp = eng.host_plan
-    log("[bench r%d] plan: %d folded rows, %d tasks, folded nnz %d (%.2fx fewer than nnz), %.1fs" % (
-        rank, hp.n_rows, hp.n_tasks, hp.folded_nnz, hp.nnz / max(1, hp.folded_nnz), time.time() - t))
+    log("[bench r%d] plan: %d list rows (%d tasks, %d folded indices), %d bitmap rows, %d perms per list CTA, %.1fs" % (
+        rank, hp.n_rows, hp.n_tasks, hp.folded_nnz, hp.n_long, hp.perms_per_cta, time.time() - t))
 
     # every rank rarefies its own permutations (numpy legacy stream, seed 12345 + rank)
     h_perms, h_perms_owner = engine.pinned_empty((perms_n, n), np.uint16)
@@ -292,7 +294,8 @@ def run_b200(args, rank, world, local_rank):
         dist.all_reduce(ms, op=dist.ReduceOp.MAX)
     ms_total = float(ms.item())
     launches = _native.launch_count() - launches0
-    row_ms, scan_ms, calls = _native.profile_read()
+    list_ms, probe_ms, scan_ms, calls = _native.profile_read()
+    row_ms = list_ms + probe_ms
     _native.profile_enable(False)
     clocks = sampler.window(w0, w1) if sampler else None
 
@@ -335,19 +338,31 @@ def run_b200(args, rank, world, local_rank):
     value = world * perms_n * args.steps / (ms_total / 1e3)
     peak, peak_src = measured_peak()
     a_perm = hp.algorithmic_bytes_per_perm
-    row_ms_per_launch = row_ms / max(1, calls)
-    achieved = a_perm * perms_n / (row_ms_per_launch / 1e3) / 1e9 if row_ms_per_launch > 0 else None
-    traffic = ncu_traffic(args.workload)
+    calls = max(1, calls)
+    # dominant kernel: the slower of the two row kernels, against ITS share of the algorithmic bytes
+    kind = "list" if list_ms >= probe_ms else "probe"
+    k_ms = (list_ms if kind == "list" else probe_ms) / calls
+    k_bytes = hp.algorithmic_bytes_of(kind)
+    achieved = k_bytes * perms_n / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
+    combined = a_perm * perms_n / (row_ms / calls / 1e3) / 1e9 if row_ms > 0 else None
+    traffic = ncu_traffic(args.workload, kind, perms_n)
     roofline = {
-        "bound": "hbm", "kernel": "minrank_kernel<8>", "achieved": achieved, "peak": peak, "unit": "GB/s",
+        "bound": "hbm", "kernel": "list_kernel<%d>" % hp.perms_per_cta if kind == "list" else "probe_kernel",
+        "achieved": achieved, "peak": peak, "unit": "GB/s",
         "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_perm": a_perm, "perms_per_launch": perms_n,
-        "ms_per_launch": row_ms_per_launch, "scan_ms_per_launch": scan_ms / max(1, calls),
+        "algorithmic_bytes_per_perm": k_bytes, "algorithmic_bytes_per_perm_whole_table": a_perm,
+        "perms_per_launch": perms_n, "ms_per_launch": k_ms,
+        "list_ms_per_launch": list_ms / calls, "probe_ms_per_launch": probe_ms / calls,
+        "scan_ms_per_launch": scan_ms / calls,
+        "row_kernels_achieved_whole_table": combined,
+        "row_kernels_frac_whole_table": combined / peak if combined else None,
         "row_kernel_share_of_step": row_ms / ms_total if ms_total > 0 else None,
         "streamed_bytes_per_row_pass": hp.streamed_bytes_per_pass,
+        "list_rows": hp.n_rows, "bitmap_rows": hp.n_long, "long_threshold": hp.long_threshold,
         "note": "algorithmic bytes = one pass over the canonical int32 gene-major CSR per permutation "
-                "(SURVEY.md 8d); the kernel streams folded uint16 rows once per 8 permutations, so "
-                "frac can exceed 1 -- see traffic and DESIGN.md",
+                "(SURVEY.md 8d), apportioned to the genes each row kernel serves; the kernels stream "
+                "2-byte folded indices once per %d permutations and bitmaps once per 64, so frac can "
+                "exceed 1 -- see traffic and DESIGN.md" % hp.perms_per_cta,
     }
     cpu = None
     if world == 1 and not args.no_cpu_baseline:

@@ -30,7 +30,7 @@
 extern "C" {
 #endif
 
-#define PGX_VERSION 100
+#define PGX_VERSION 200
 
 enum {
     PGX_OK = 0,
@@ -41,27 +41,44 @@ enum {
 
 /* Device-resident plan of a BINARY gene x genome presence/absence table, built once per
  * matrix by the host (pangenomix_b200/plan.py) from ``df_genes.data`` -- the same object
- * estimate_pan_core_size reads at pangenome_analysis.py:74.  Rows are "folded": each
- * general gene stores the SHORTER of its present-genome list and its absent-genome list
- * as sorted uint16 genome indices in 16-byte chunks (8 indices, padded with the sentinel
- * index n_genomes).  Genes that are empty, universal, present in exactly one genome or
- * absent from exactly one genome never reach the row kernel: they are closed forms of the
- * permutation and are folded into the per-genome weight vectors below. */
+ * estimate_pan_core_size reads at pangenome_analysis.py:74.  Genes fall into three groups:
+ *
+ *  closed forms  Empty, universal, single-genome and single-absence genes never reach a row
+ *                kernel: they are functions of perm[0] and of one rank and live in the
+ *                per-genome vectors d_colsum / d_w_present / d_w_absent.
+ *  list rows     Every other gene whose SHORTER list (present genomes or absent genomes) has
+ *                fewer than the plan's long threshold entries stores that list as uint16
+ *                genome indices in 16-byte chunks.  A warp task is up to 32 rows with the
+ *                same chunk count and list kind, one lane per row; lane l reads chunk
+ *                first_chunk + it * 32 + l at iteration it.  Unused slots hold sentinel
+ *                indices in [N, N + 32) whose rank-table entry is 0xffff.  Entries are
+ *                ordered inside a row so that neighbouring lanes gather from different
+ *                shared-memory banks.  d_sorted_* hold the same lists plainly sorted.
+ *  bitmap rows   The remaining (long) genes, as a genome-major bit-sliced bitmap: rows are
+ *                grouped in superblocks of 1,024; d_bits[(sb * N + c) * 32 + w] holds, in bit b,
+ *                the presence of row sb * 1024 + 32 w + b in genome c (one 128-byte line per
+ *                (superblock, genome)).  Rows of similar density share a superblock.
+ */
 typedef struct pgx_plan {
-    const uint16_t *d_chunks;    /* [n_chunks * 8] folded genome indices, 16-byte aligned */
-    const int32_t *d_row_ptr;    /* [n_rows + 1]   first chunk of every folded row */
-    const int32_t *d_tasks;      /* [n_tasks * 2]  {first_row, n_rows<<8 | log2(lanes)<<1 | absent_list} */
-    const int32_t *d_w_present;  /* [n_genomes]    #genes present ONLY in genome c */
-    const int32_t *d_w_absent;   /* [n_genomes]    #genes absent ONLY from genome c */
+    const uint16_t *d_chunks;      /* [n_chunks * 8] list rows, 16-byte aligned */
+    const int32_t *d_tasks;        /* [n_tasks * 4] {first_chunk, chunks_per_row | rows << 16 | absent_list << 24,
+                                      first_row, 0}, 16-byte aligned, costly tasks first */
+    const uint16_t *d_sorted_idx;  /* sorted copy of the list rows */
+    const int32_t *d_sorted_ptr;   /* [n_rows + 1] offsets into d_sorted_idx */
+    const uint32_t *d_bits;        /* [n_superblocks * n_genomes * 32] bit-sliced bitmap rows, 16-byte aligned */
+    const void *reserved_ptr;
+    const int32_t *d_colsum;       /* [n_genomes] #genes present in genome c (all genes of the table) */
+    const int32_t *d_w_present;    /* [n_genomes] #genes present ONLY in genome c */
+    const int32_t *d_w_absent;     /* [n_genomes] #genes absent ONLY from genome c */
     int64_t n_chunks;
-    int32_t n_genomes;           /* N  (1 <= N <= 65535) */
-    int32_t n_genes;             /* G  (all genes of the table, incl. closed-form ones) */
-    int32_t n_rows;              /* folded rows that go through the row kernel */
+    int32_t n_genomes;             /* N  (1 <= N <= 65503) */
+    int32_t n_genes;               /* G  (all genes of the table, incl. closed-form ones) */
+    int32_t n_rows;                /* list rows */
     int32_t n_tasks;
-    int32_t n_empty;             /* genes present in no genome */
-    int32_t n_full;              /* genes present in every genome */
-    int32_t sum_w_present;
-    int32_t sum_w_absent;
+    int32_t n_long;                /* bitmap rows */
+    int32_t n_superblocks;         /* ceil(n_long / 1024) */
+    int32_t perms_per_cta;         /* 8, 4, 2 or 1: rank tables that share a CTA's shared memory */
+    int32_t reserved;
 } pgx_plan;
 
 int pgx_version(void);
@@ -91,16 +108,16 @@ int pgx_pan_core_curves_f64(const pgx_plan *plan, const uint16_t *d_perms, int64
 int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int64_t n_perm,
                              void *h_curves, int32_t out_f64, int64_t perms_per_block);
 
-/* Launch-shape overrides for experiments (0 = heuristic): permutations per CTA
- * (1, 2, 4 or 8) and row splits per permutation batch. */
+/* Launch-shape overrides for experiments (0 = heuristic): permutations per CTA of the list
+ * kernel (1, 2, 4 or 8), row splits per permutation batch and threads per CTA. */
 int pgx_set_tuning(int32_t perms_per_cta, int32_t row_splits, int32_t threads_per_cta);
 
 /* Per-kernel timing for roofline reports: while enabled, every pgx_pan_core_curves*
- * call brackets its row kernel and its scan kernel with CUDA events on the caller's
- * stream.  pgx_profile_read waits for them, returns the summed durations (ms) and the
- * number of calls since the last read, and releases the events. */
+ * call brackets its list kernel, its bitmap-probe kernel and its scan kernel with CUDA
+ * events on the caller's stream.  pgx_profile_read waits for them, returns the summed
+ * durations (ms) and the number of calls since the last read, and releases the events. */
 int pgx_profile_enable(int32_t on);
-int pgx_profile_read(double *minrank_ms, double *scan_ms, int64_t *calls);
+int pgx_profile_read(double *list_ms, double *probe_ms, double *scan_ms, int64_t *calls);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */
 int64_t pgx_launch_count(void);

@@ -28,8 +28,12 @@ class PgxPlan(ctypes.Structure):
     """Mirror of ``struct pgx_plan`` (include/pgx.h)."""
     _fields_ = [
         ("d_chunks", ctypes.c_void_p),
-        ("d_row_ptr", ctypes.c_void_p),
         ("d_tasks", ctypes.c_void_p),
+        ("d_sorted_idx", ctypes.c_void_p),
+        ("d_sorted_ptr", ctypes.c_void_p),
+        ("d_bits", ctypes.c_void_p),
+        ("reserved_ptr", ctypes.c_void_p),
+        ("d_colsum", ctypes.c_void_p),
         ("d_w_present", ctypes.c_void_p),
         ("d_w_absent", ctypes.c_void_p),
         ("n_chunks", ctypes.c_int64),
@@ -37,10 +41,10 @@ class PgxPlan(ctypes.Structure):
         ("n_genes", ctypes.c_int32),
         ("n_rows", ctypes.c_int32),
         ("n_tasks", ctypes.c_int32),
-        ("n_empty", ctypes.c_int32),
-        ("n_full", ctypes.c_int32),
-        ("sum_w_present", ctypes.c_int32),
-        ("sum_w_absent", ctypes.c_int32),
+        ("n_long", ctypes.c_int32),
+        ("n_superblocks", ctypes.c_int32),
+        ("perms_per_cta", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
     ]
 
 
@@ -85,7 +89,7 @@ def load():
     lib.pgx_profile_enable.argtypes = [i32]
     lib.pgx_profile_read.restype = ctypes.c_int
     lib.pgx_profile_read.argtypes = [ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
-                                     ctypes.POINTER(i64)]
+                                     ctypes.POINTER(ctypes.c_double), ctypes.POINTER(i64)]
     _lib = lib
     return lib
 
@@ -105,10 +109,10 @@ def profile_enable(on=True):
 
 
 def profile_read():
-    """(row-kernel ms, scan-kernel ms, calls) accumulated since the last read."""
-    a, b, c = ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
-    check(load().pgx_profile_read(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c)))
-    return a.value, b.value, c.value
+    """(list-kernel ms, probe-kernel ms, scan-kernel ms, calls) accumulated since the last read."""
+    a, b, c, d = ctypes.c_double(), ctypes.c_double(), ctypes.c_double(), ctypes.c_int64()
+    check(load().pgx_profile_read(ctypes.byref(a), ctypes.byref(b), ctypes.byref(c), ctypes.byref(d)))
+    return a.value, b.value, c.value, d.value
 
 
 def set_tuning(perms_per_cta=0, row_splits=0, threads_per_cta=0):

@@ -7,20 +7,23 @@
 //   pan[k]  = #{g : fp_g <= k} = cumsum(hist(fp))[k]
 //   core[k] = #{g : fa_g >  k} = G - cumsum(hist(fa))[k]
 // (bit-exact with :89-:90; the identity itself is under test in tests/test_oracle_golden.py).
+// Exactly one of fp_g, fa_g is 0 -- the rank-0 genome either has the gene or not -- so bin 0
+// of both histograms is a column sum of the table (closed form); the row kernels only ever
+// produce the ONE non-zero statistic of every (gene, permutation).
 //
-// Kernel 1 (minrank_kernel<B>): a CTA stages the rank tables of B permutations in shared
-//   memory as T[genome][B] uint16 -- one 16-byte line per genome for B = 8 -- streams the
-//   folded index chunks of its share of the rows with 128-bit no-allocate loads, and for
-//   every index does ONE shared-memory gather that serves all B permutations, folding it
-//   into packed uint16x2 running minima (VIMNMX.U16x2).  Rows are served by 1..32 lanes
-//   according to their length class; the lanes of a row combine with a shuffle butterfly.
-//   The streamed list yields one statistic directly (its min rank); the other one is the
-//   mex of the streamed ranks, which is 0 unless the min is 0 -- then it is found by
-//   probing genomes in rank order with a binary search of the sorted list (rare).
-//   Results go straight into the output rows, used as per-permutation histograms.
-// Kernel 2 (scan_kernel): adds the closed-form gene classes (empty / universal /
-//   single-genome / single-absence genes are functions of perm[0] and perm[k] only) and
-//   turns each histogram into its curve with a block-wide prefix scan, in place.
+// Kernel 1 (list_kernel<B>): genes with a short list.  A CTA stages the rank tables of B
+//   permutations in shared memory as T[genome][B] uint16 -- one 16-byte line per genome for
+//   B = 8 -- and its warps pull tasks of 32 rows, one lane per row.  Every index costs ONE
+//   shared-memory gather that serves all B permutations, folded into packed uint16x2
+//   running minima (VIMNMX.U16x2).  The host ordered the indices of a row so that the
+//   lanes of a wavefront hit distinct banks.  If the min is 0 the wanted statistic is the
+//   mex of the list's ranks instead (probe genomes in rank order against the sorted copy).
+// Kernel 2 (probe_kernel): genes with long lists, stored as a genome-major, bit-sliced
+//   bitmap (32 genes per word).  A warp walks one genome order for 1,024 genes at once, one
+//   coalesced 128-byte line per step; the first genome whose bit differs from the rank-0
+//   genome's bit is the gene's statistic.  O(N / m) steps instead of O(m) gathers.
+// Kernel 3 (scan_kernel): adds the closed-form gene classes and turns each histogram into
+//   its curve with a block-wide prefix scan, in place.
 #include <mutex>
 #include <vector>
 
@@ -30,8 +33,9 @@ namespace pgx {
 
 namespace {
 
-// Optional CUDA-event brackets around the two kernels of every call (bench.py's roofline).
-struct ProfileEvents { cudaEvent_t begin, mid, end; };
+constexpr int SENTINELS = 32;          // rank-table rows N .. N+31 hold 0xffff (plan.py)
+// Optional CUDA-event brackets around the kernels of every call (bench.py's roofline).
+struct ProfileEvents { cudaEvent_t begin, list_done, probe_done, end; };
 bool g_profile_on = false;
 std::mutex g_profile_mu;
 std::vector<ProfileEvents> g_profile_events;
@@ -47,13 +51,6 @@ template <int B>
 struct Packed {
     static constexpr int REGS = (B + 1) / 2;
 };
-
-template <int B>
-__device__ __forceinline__ uint32_t pmin(uint32_t x, uint32_t y)
-{
-    if constexpr (B == 1) return min(x, y);
-    return __vminu2(x, y);
-}
 
 // One gather of the B ranks of genome c, folded into the running minima.
 template <int B>
@@ -78,6 +75,20 @@ __device__ __forceinline__ void gather_min(const uint16_t *table, uint32_t c,
     }
 }
 
+template <int B>
+__device__ __forceinline__ void gather_chunk(const uint16_t *table, const uint4 v,
+                                             uint32_t (&acc)[Packed<B>::REGS])
+{
+    gather_min<B>(table, v.x & 0xffffu, acc);
+    gather_min<B>(table, v.x >> 16, acc);
+    gather_min<B>(table, v.y & 0xffffu, acc);
+    gather_min<B>(table, v.y >> 16, acc);
+    gather_min<B>(table, v.z & 0xffffu, acc);
+    gather_min<B>(table, v.z >> 16, acc);
+    gather_min<B>(table, v.w & 0xffffu, acc);
+    gather_min<B>(table, v.w >> 16, acc);
+}
+
 // mex of the ranks of a sorted genome list, given that rank 0 is in it: walk the genome
 // order from rank 1 and stop at the first genome that is not in the list.
 __device__ __noinline__ int mex_probe(const uint16_t *__restrict__ perm,
@@ -96,12 +107,15 @@ __device__ __noinline__ int mex_probe(const uint16_t *__restrict__ perm,
     return k;
 }
 
+// Deferred mex events of a warp: (list row << 4 | absent_list << 3 | permutation slot).
+constexpr int EVENT_QUEUE = 64;
+
 template <int B>
-__global__ void __launch_bounds__(1024)
-minrank_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long long n_perm,
-               int32_t *__restrict__ hist)
+__global__ void __launch_bounds__(1024, 1)
+list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long long n_perm,
+            int32_t *__restrict__ hist)
 {
-    extern __shared__ __align__(16) uint16_t table[];   // [(N + 1)][B]
+    extern __shared__ __align__(16) uint16_t table[];   // [(N + 32)][B], then the warps' event queues
     __shared__ int s_next_task;
 
     constexpr int REGS = Packed<B>::REGS;
@@ -110,6 +124,8 @@ minrank_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const lo
     const int lane = tid & 31;
     const long long p0 = static_cast<long long>(blockIdx.y) * B;
     const int n_valid = static_cast<int>(min(static_cast<long long>(B), n_perm - p0));
+    uint32_t *queue = reinterpret_cast<uint32_t *>(table + ((static_cast<size_t>(n + SENTINELS) * B + 7) & ~size_t(7))) +
+                      (tid >> 5) * EVENT_QUEUE;
 
     // ---- stage the inverse permutations: T[perm[k]][q] = k ----
     for (int q = 0; q < B; ++q) {
@@ -120,92 +136,143 @@ minrank_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const lo
             for (int k = tid; k < n; k += blockDim.x) table[k * B + q] = 0xffffu;
         }
     }
-    if (tid < B) table[n * B + tid] = 0xffffu;   // padding index N never wins a min
+    for (int k = tid; k < SENTINELS * B; k += blockDim.x) table[n * B + k] = 0xffffu;   // never win a min
     if (tid == 0) s_next_task = 0;
     __syncthreads();
 
     const uint4 *__restrict__ chunks = reinterpret_cast<const uint4 *>(plan.d_chunks);
-    const int2 *__restrict__ tasks = reinterpret_cast<const int2 *>(plan.d_tasks);
+    const int4 *__restrict__ tasks = reinterpret_cast<const int4 *>(plan.d_tasks);
     const long long row_stride = 2ll * n;
+    int queued = 0;                                       // warp-uniform
 
-    uint32_t zero_pan[B], zero_core[B];   // warp-uniform counts of "other statistic == 0"
-#pragma unroll
-    for (int q = 0; q < B; ++q) { zero_pan[q] = 0; zero_core[q] = 0; }
-
-    for (;;) {
+    auto next_task = [&]() -> int4 {
         int t = 0;
         if (lane == 0) t = atomicAdd(&s_next_task, 1);
         t = __shfl_sync(FULL_MASK, t, 0);
         const long long task = static_cast<long long>(t) * gridDim.x + blockIdx.x;
-        if (task >= plan.n_tasks) break;
+        return task < plan.n_tasks ? __ldg(tasks + task) : make_int4(0, 0, 0, 0);
+    };
+    // mex of one queued (row, permutation): all lanes of the warp work on different events
+    auto resolve = [&](uint32_t ev) {
+        const int q = ev & 7, row = ev >> 4;
+        const int s0 = plan.d_sorted_ptr[row];
+        const int k = mex_probe(perms + (p0 + q) * n, plan.d_sorted_idx + s0, plan.d_sorted_ptr[row + 1] - s0, n);
+        // present list: min -> pan histogram, mex -> core histogram; absent list: swapped.
+        if (k < n) atomicAdd(hist + (p0 + q) * row_stride + ((ev & 8) ? 0 : n) + k, 1);
+    };
 
-        const int2 td = tasks[task];
-        const int log_w = (td.y >> 1) & 7;
-        const int absent_list = td.y & 1;
-        const int n_rows = td.y >> 8;
-        const int w = 1 << log_w;
-        const int group = lane >> log_w;
-        const int lig = lane & (w - 1);
-        const bool valid = group < n_rows;
-        const int row = td.x + (valid ? group : 0);
-        const int c0 = plan.d_row_ptr[row];
-        const int c1 = valid ? plan.d_row_ptr[row + 1] : c0;
+    // Two tasks ahead: descriptor of task i+2 and first chunk of task i+1 are in flight
+    // while task i is gathered.
+    int4 td = next_task();
+    int4 td_next = next_task();
+    uint4 cur = make_uint4(0, 0, 0, 0);
+    if (td.y & 0xffff) cur = ldg_stream(chunks + td.x + lane);
+    while (td.y & 0xffff) {
+        const int4 td_after = next_task();
+        uint4 first_next = make_uint4(0, 0, 0, 0);
+        if (td_next.y & 0xffff) first_next = ldg_stream(chunks + td_next.x + lane);
+
+        const int nch = td.y & 0xffff;
+        const int n_rows = (td.y >> 16) & 0xff;
+        const uint32_t absent_list = (td.y >> 24) & 1;
+        const uint4 *cp = chunks + td.x + lane;
 
         uint32_t acc[REGS];
 #pragma unroll
         for (int i = 0; i < REGS; ++i) acc[i] = 0xffffffffu;
-
-#pragma unroll 2
-        for (int ch = c0 + lig; ch < c1; ch += w) {
-            const uint4 v = ldg_stream(chunks + ch);
-            gather_min<B>(table, v.x & 0xffffu, acc);
-            gather_min<B>(table, v.x >> 16, acc);
-            gather_min<B>(table, v.y & 0xffffu, acc);
-            gather_min<B>(table, v.y >> 16, acc);
-            gather_min<B>(table, v.z & 0xffffu, acc);
-            gather_min<B>(table, v.z >> 16, acc);
-            gather_min<B>(table, v.w & 0xffffu, acc);
-            gather_min<B>(table, v.w >> 16, acc);
+        for (int it = 1; it < nch; ++it) {
+            const uint4 nxt = ldg_stream(cp + it * 32);
+            gather_chunk<B>(table, cur, acc);
+            cur = nxt;
         }
-        for (int off = w >> 1; off > 0; off >>= 1) {
-#pragma unroll
-            for (int i = 0; i < REGS; ++i)
-                acc[i] = pmin<B>(acc[i], __shfl_xor_sync(FULL_MASK, acc[i], off));
-        }
+        gather_chunk<B>(table, cur, acc);
 
-        // present list: min -> pan histogram, mex -> core histogram; absent list: swapped.
+        const bool valid = lane < n_rows;
         int32_t *list_hist = hist + (absent_list ? n : 0);
-        int32_t *other_hist = hist + (absent_list ? 0 : n);
 #pragma unroll
         for (int q = 0; q < B; ++q) {
             if (q < n_valid) {
                 uint32_t mn;
                 if constexpr (B == 1) mn = acc[0] & 0xffffu;
                 else mn = (acc[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
-                const bool mine = valid && (lig == (q & (w - 1)));
-                if (mine) {
-                    const long long base = (p0 + q) * row_stride;
-                    atomicAdd(list_hist + base + mn, 1);
-                    if (mn == 0) {
-                        const int k = mex_probe(perms + (p0 + q) * n, plan.d_chunks + 8ll * c0,
-                                                (c1 - c0) * 8, n);
-                        if (k < n) atomicAdd(other_hist + base + k, 1);
+                if (valid && mn != 0) atomicAdd(list_hist + (p0 + q) * row_stride + mn, 1);
+                // min == 0: the wanted statistic is the mex; queue it, resolve 32 at a time
+                const bool ev = valid && mn == 0;
+                const uint32_t m = __ballot_sync(FULL_MASK, ev);
+                if (m) {
+                    if (ev) queue[queued + __popc(m & ((1u << lane) - 1u))] =
+                        (static_cast<uint32_t>(td.z + lane) << 4) | (absent_list << 3) | q;
+                    queued += __popc(m);
+                    __syncwarp();
+                    if (queued >= 32) {
+                        queued -= 32;
+                        const uint32_t e = queue[queued + lane];
+                        __syncwarp();
+                        resolve(e);
                     }
                 }
-                const uint32_t nz = __popc(__ballot_sync(FULL_MASK, mine && mn != 0));
-                if (absent_list) zero_pan[q] += nz; else zero_core[q] += nz;
             }
         }
+        td = td_next;
+        cur = first_next;
+        td_next = td_after;
     }
+    if (lane < queued) resolve(queue[lane]);
+}
 
-    if (lane == 0) {
+// Bitmap rows, bit-sliced: 32 genes per word, genome-major.  A warp owns one superblock of
+// 1,024 bitmap rows and one permutation; lane l holds rows 32 l .. 32 l + 31 of the
+// superblock as one word.  Walking the genome order, step k loads ONE coalesced 128-byte line
+// -- the presence bits of all 1,024 genes in genome perm[k] -- and
+//     flipped = (line ^ line_of_rank_0) & pending
+// marks the genes whose bit differs from the rank-0 genome's for the first time: k is their
+// statistic (first presence if the rank-0 bit was 0, first absence if it was 1).  The walk
+// stops when no gene of the superblock is pending: O(N / m) steps of O(1) work per 32 genes,
+// the reference's own genome-by-genome accumulation (:87-:90) restricted to unresolved genes.
+constexpr int SLICE_WARPS = 4;
+constexpr int SLICE_DEPTH = 8;         // lines in flight per warp
+
+__global__ void __launch_bounds__(SLICE_WARPS * 32, 8)
+probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long long n_perm,
+             int32_t *__restrict__ hist)
+{
+    const int n = plan.n_genomes;
+    const int lane = threadIdx.x & 31;
+    const long long unit = static_cast<long long>(blockIdx.x) * SLICE_WARPS + (threadIdx.x >> 5);
+    if (unit >= n_perm * plan.n_superblocks) return;           // whole warps leave together
+    const long long sb = unit / n_perm, q = unit - sb * n_perm;   // costly superblocks first
+
+    const uint32_t *__restrict__ lines = plan.d_bits + (static_cast<size_t>(sb) * n) * 32 + lane;
+    const uint16_t *__restrict__ perm = perms + q * n;
+    int32_t *out = hist + q * 2ll * n + (lane == 1 ? n : 0);      // lane 0 adds pan counts, lane 1 core counts
+
+    const long long first_row = sb * 1024 + lane * 32;
+    const long long left = static_cast<long long>(plan.n_long) - first_row;
+    uint32_t pending = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+    const uint32_t b0 = __ldg(lines + static_cast<size_t>(perm[0]) * 32);
+
+    for (int k0 = 0; k0 < n; k0 += 32) {
+        const uint32_t chunk = k0 + lane < n ? perm[k0 + lane] : 0u;      // genomes of ranks k0 .. k0 + 31
+#pragma unroll 1
+        for (int j0 = 0; j0 < 32; j0 += SLICE_DEPTH) {
+            uint32_t w[SLICE_DEPTH];
 #pragma unroll
-        for (int q = 0; q < B; ++q) {
-            if (q < n_valid) {
-                const long long base = (p0 + q) * row_stride;
-                if (zero_pan[q]) atomicAdd(hist + base, static_cast<int>(zero_pan[q]));
-                if (zero_core[q]) atomicAdd(hist + base + n, static_cast<int>(zero_core[q]));
+            for (int j = 0; j < SLICE_DEPTH; ++j) {
+                const uint32_t c = __shfl_sync(FULL_MASK, chunk, j0 + j);
+                w[j] = __ldg(lines + static_cast<size_t>(c) * 32);
             }
+#pragma unroll
+            for (int j = 0; j < SLICE_DEPTH; ++j) {
+                const int k = k0 + j0 + j;
+                const uint32_t flipped = k < n ? (w[j] ^ b0) & pending : 0u;
+                pending &= ~flipped;
+                // low half: genes first seen at k (pan side); high half: genes first missed at k (core side)
+                const uint32_t packed = __popc(flipped & ~b0) | (__popc(flipped & b0) << 16);
+                const uint32_t total = __reduce_add_sync(FULL_MASK, packed);
+                const uint32_t mine = lane == 1 ? total >> 16 : total & 0xffffu;
+                if (lane < 2 && mine) atomicAdd(out + k, static_cast<int>(mine));
+            }
+            if (!__any_sync(FULL_MASK, pending)) return;
         }
     }
 }
@@ -225,15 +292,15 @@ scan_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const int32
     const int32_t *h = hist + p * 2ll * n + static_cast<long long>(side) * n;
     OutT *o = out + p * 2ll * n + static_cast<long long>(side) * n;
     const uint16_t *perm = perms + p * n;
-    // genes living in / missing from a single genome c: the list-side statistic is rank[c],
+    // Closed forms.  Bin 0: genes present in (pan) / absent from (core) the first genome.
+    // Genes living in / missing from a single genome c: the list-side statistic is rank[c];
     // the other one is 1 if c comes first and 0 otherwise.
     const int32_t *w_list = side == 0 ? plan.d_w_present : plan.d_w_absent;
     const int32_t *w_other = side == 0 ? plan.d_w_absent : plan.d_w_present;
     const int first = perm[0];
-    const int other_first = w_other[first];
-    const int add0 = side == 0 ? plan.n_full + (plan.sum_w_absent - other_first)
-                               : plan.n_empty + (plan.sum_w_present - other_first);
-    const int add1 = other_first;
+    const int col_first = plan.d_colsum[first];
+    const int bin0 = side == 0 ? col_first : plan.n_genes - col_first;
+    const int add1 = w_other[first];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     int carry = 0;
@@ -245,9 +312,8 @@ scan_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const int32
             const int k = base + tid * ITEMS + i;
             int x = 0;
             if (k < n) {
-                x = h[k] + w_list[perm[k]];
-                if (k == 0) x += add0;
-                if (k == 1) x += add1;
+                if (k == 0) x = bin0;
+                else x = h[k] + w_list[perm[k]] + (k == 1 ? add1 : 0);
             }
             run += x;
             v[i] = run;
@@ -284,17 +350,22 @@ scan_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const int32
 int check_plan(const pgx_plan *plan)
 {
     if (!plan) return fail(PGX_ERR_INVALID, "plan is null");
-    if (plan->n_genomes < 1 || plan->n_genomes > 65535)
-        return fail(PGX_ERR_UNSUPPORTED, "n_genomes = %d outside 1..65535 (uint16 genome indices)",
+    if (plan->n_genomes < 1 || plan->n_genomes > 65503)
+        return fail(PGX_ERR_UNSUPPORTED, "n_genomes = %d outside 1..65503 (uint16 genome indices)",
                     plan->n_genomes);
-    if (plan->n_genes < 0 || plan->n_rows < 0 || plan->n_tasks < 0 || plan->n_chunks < 0)
+    if (plan->n_genes < 0 || plan->n_rows < 0 || plan->n_tasks < 0 || plan->n_chunks < 0 || plan->n_long < 0)
         return fail(PGX_ERR_INVALID, "negative size in plan");
-    if (!plan->d_w_present || !plan->d_w_absent)
-        return fail(PGX_ERR_INVALID, "plan weight vectors are null");
-    if (plan->n_tasks > 0 && (!plan->d_chunks || !plan->d_row_ptr || !plan->d_tasks))
-        return fail(PGX_ERR_INVALID, "plan has tasks but null row arrays");
-    if (reinterpret_cast<uintptr_t>(plan->d_chunks) & 15)
-        return fail(PGX_ERR_INVALID, "d_chunks must be 16-byte aligned");
+    if (!plan->d_w_present || !plan->d_w_absent || !plan->d_colsum)
+        return fail(PGX_ERR_INVALID, "plan closed-form vectors are null");
+    if (plan->n_tasks > 0 && (!plan->d_chunks || !plan->d_tasks || !plan->d_sorted_idx || !plan->d_sorted_ptr))
+        return fail(PGX_ERR_INVALID, "plan has list tasks but null list arrays");
+    if (plan->n_long > 0 && !plan->d_bits)
+        return fail(PGX_ERR_INVALID, "plan has bitmap rows but a null bitmap");
+    if (plan->n_superblocks != (plan->n_long + 1023) / 1024)
+        return fail(PGX_ERR_INVALID, "n_superblocks must be ceil(n_long / 1024)");
+    if ((reinterpret_cast<uintptr_t>(plan->d_chunks) | reinterpret_cast<uintptr_t>(plan->d_tasks) |
+         reinterpret_cast<uintptr_t>(plan->d_bits)) & 15)
+        return fail(PGX_ERR_INVALID, "d_chunks, d_tasks and d_bits must be 16-byte aligned");
     return PGX_OK;
 }
 
@@ -319,15 +390,16 @@ int device_limits(DeviceLimits *out)
 }
 
 template <int B>
-int launch_minrank(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm, int32_t *d_hist,
-                   const DeviceLimits &lim, cudaStream_t stream)
+int launch_list(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm, int32_t *d_hist,
+                const DeviceLimits &lim, cudaStream_t stream)
 {
-    const size_t smem = static_cast<size_t>(plan.n_genomes + 1) * B * sizeof(uint16_t);
-    PGX_CUDA(cudaFuncSetAttribute(minrank_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
     int threads = g_tuning.threads;
-    if (threads <= 0) threads = smem > 100 * 1024 ? 1024 : (smem > 40 * 1024 ? 512 : 256);
+    const size_t table_bytes = ((static_cast<size_t>(plan.n_genomes + SENTINELS) * B + 7) & ~size_t(7)) * sizeof(uint16_t);
+    if (threads <= 0) threads = table_bytes > 100 * 1024 ? 1024 : (table_bytes > 40 * 1024 ? 512 : 256);
     threads = max(32, min(1024, (threads / 32) * 32));
+    const size_t smem = table_bytes + static_cast<size_t>(threads / 32) * EVENT_QUEUE * sizeof(uint32_t);
+    PGX_CUDA(cudaFuncSetAttribute(list_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                  static_cast<int>(smem)));
     const long long batches = (n_perm + B - 1) / B;
     // Row splits: enough CTAs for ~16 waves so the tail is small, but every CTA keeps at
     // least a few tasks per warp (the table build is amortised over them).
@@ -336,7 +408,7 @@ int launch_minrank(const pgx_plan &plan, const uint16_t *d_perms, long long n_pe
         const long long resident = static_cast<long long>(lim.sm_count) *
                                    max(1, min(8, static_cast<int>((200 * 1024) / (smem + 1024))));
         const long long want = (16 * resident + batches - 1) / batches;
-        const long long most = max(1ll, static_cast<long long>(plan.n_tasks) / ((threads / 32) * 4));
+        const long long most = max(1ll, static_cast<long long>(plan.n_tasks) / ((threads / 32) * 2));
         splits = static_cast<int>(max(1ll, min(want, most)));
     }
     splits = max(1, min(splits, 65535));
@@ -345,11 +417,23 @@ int launch_minrank(const pgx_plan &plan, const uint16_t *d_perms, long long n_pe
     for (long long b0 = 0; b0 < batches; b0 += 65535) {
         const long long nb = min(65535ll, batches - b0);
         dim3 grid(static_cast<unsigned>(splits), static_cast<unsigned>(nb));
-        minrank_kernel<B><<<grid, threads, smem, stream>>>(plan, d_perms + b0 * B * plan.n_genomes,
-                                                            n_perm - b0 * B,
-                                                            d_hist + b0 * B * 2ll * plan.n_genomes);
-        PGX_LAUNCH_CHECK("minrank_kernel");
+        list_kernel<B><<<grid, threads, smem, stream>>>(plan, d_perms + b0 * B * plan.n_genomes,
+                                                         n_perm - b0 * B,
+                                                         d_hist + b0 * B * 2ll * plan.n_genomes);
+        PGX_LAUNCH_CHECK("list_kernel");
     }
+    return PGX_OK;
+}
+
+int launch_probe(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm, int32_t *d_hist,
+                 cudaStream_t stream)
+{
+    // one warp per (superblock, permutation); 2^31 blocks of 4 warps cover any realistic call
+    const long long units = n_perm * plan.n_superblocks;
+    const long long blocks = (units + SLICE_WARPS - 1) / SLICE_WARPS;
+    if (blocks > 2147483647ll) return fail(PGX_ERR_UNSUPPORTED, "too many (superblock, permutation) units in one call");
+    probe_kernel<<<static_cast<unsigned>(blocks), SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, d_hist);
+    PGX_LAUNCH_CHECK("probe_kernel");
     return PGX_OK;
 }
 
@@ -369,27 +453,33 @@ int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, 
     const bool profile = g_profile_on;
     if (profile) {
         PGX_CUDA(cudaEventCreate(&ev.begin));
-        PGX_CUDA(cudaEventCreate(&ev.mid));
+        PGX_CUDA(cudaEventCreate(&ev.list_done));
+        PGX_CUDA(cudaEventCreate(&ev.probe_done));
         PGX_CUDA(cudaEventCreate(&ev.end));
         PGX_CUDA(cudaEventRecord(ev.begin, stream));
     }
     if (plan->n_tasks > 0) {
-        const size_t per_perm = static_cast<size_t>(n + 1) * sizeof(uint16_t);
-        const size_t budget = static_cast<size_t>(lim.smem_optin) - 64;
+        const size_t per_perm = static_cast<size_t>(n + SENTINELS) * sizeof(uint16_t);
+        const size_t budget = static_cast<size_t>(lim.smem_optin) - 64 - 32 * EVENT_QUEUE * sizeof(uint32_t);
         int b = g_tuning.perms_per_cta;
+        if (b != 1 && b != 2 && b != 4 && b != 8) b = plan->perms_per_cta;
         if (b != 1 && b != 2 && b != 4 && b != 8) b = 8;
         while (b > 1 && per_perm * b > budget) b >>= 1;
         if (per_perm * b > budget) return fail(PGX_ERR_UNSUPPORTED, "rank table does not fit shared memory");
         int rc;
         switch (b) {
-            case 8: rc = launch_minrank<8>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
-            case 4: rc = launch_minrank<4>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
-            case 2: rc = launch_minrank<2>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
-            default: rc = launch_minrank<1>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
+            case 8: rc = launch_list<8>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
+            case 4: rc = launch_list<4>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
+            case 2: rc = launch_list<2>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
+            default: rc = launch_list<1>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
         }
         if (rc) return rc;
     }
-    if (profile) PGX_CUDA(cudaEventRecord(ev.mid, stream));
+    if (profile) PGX_CUDA(cudaEventRecord(ev.list_done, stream));
+    if (plan->n_long > 0) {
+        if (int rc = launch_probe(*plan, d_perms, n_perm, d_hist, stream)) return rc;
+    }
+    if (profile) PGX_CUDA(cudaEventRecord(ev.probe_done, stream));
     for (long long p0 = 0; p0 < n_perm; p0 += 2147483647ll) {
         const long long np = min(2147483647ll, n_perm - p0);
         dim3 grid(static_cast<unsigned>(np), 2);
@@ -515,23 +605,27 @@ int pgx_profile_enable(int32_t on)
     return PGX_OK;
 }
 
-int pgx_profile_read(double *minrank_ms, double *scan_ms, int64_t *calls)
+int pgx_profile_read(double *list_ms, double *probe_ms, double *scan_ms, int64_t *calls)
 {
     std::lock_guard<std::mutex> lock(pgx::g_profile_mu);
-    double a = 0.0, b = 0.0;
+    double a = 0.0, b = 0.0, c = 0.0;
     for (auto &ev : pgx::g_profile_events) {
-        float t0 = 0.f, t1 = 0.f;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
         PGX_CUDA(cudaEventSynchronize(ev.end));
-        PGX_CUDA(cudaEventElapsedTime(&t0, ev.begin, ev.mid));
-        PGX_CUDA(cudaEventElapsedTime(&t1, ev.mid, ev.end));
+        PGX_CUDA(cudaEventElapsedTime(&t0, ev.begin, ev.list_done));
+        PGX_CUDA(cudaEventElapsedTime(&t1, ev.list_done, ev.probe_done));
+        PGX_CUDA(cudaEventElapsedTime(&t2, ev.probe_done, ev.end));
         a += t0;
         b += t1;
+        c += t2;
         cudaEventDestroy(ev.begin);
-        cudaEventDestroy(ev.mid);
+        cudaEventDestroy(ev.list_done);
+        cudaEventDestroy(ev.probe_done);
         cudaEventDestroy(ev.end);
     }
-    if (minrank_ms) *minrank_ms = a;
-    if (scan_ms) *scan_ms = b;
+    if (list_ms) *list_ms = a;
+    if (probe_ms) *probe_ms = b;
+    if (scan_ms) *scan_ms = c;
     if (calls) *calls = static_cast<int64_t>(pgx::g_profile_events.size());
     pgx::g_profile_events.clear();
     return PGX_OK;

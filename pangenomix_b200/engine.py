@@ -88,32 +88,38 @@ class PanCoreEngine:
     ``data`` is ``df_genes.data`` (scipy COO gene x genome, pangenome_analysis.py:74).
     """
 
-    def __init__(self, data, device=None, host_plan: HostPlan | None = None):
+    def __init__(self, data, device=None, host_plan: HostPlan | None = None, long_threshold=None):
         torch = _torch()
         self.device = _require_cuda(device)
         self.lib = _native.load()
-        self.host_plan = host_plan if host_plan is not None else build_host_plan(data)
+        if host_plan is None:
+            if long_threshold is None and os.environ.get("PGX_LONG_THRESHOLD"):
+                long_threshold = int(os.environ["PGX_LONG_THRESHOLD"])
+            host_plan = build_host_plan(data, long_threshold=long_threshold)
+        self.host_plan = host_plan
         hp = self.host_plan
         self.n_genes, self.n_genomes = hp.n_genes, hp.n_genomes
 
         def up(arr, as_dtype):
-            t = torch.from_numpy(np.ascontiguousarray(arr).view(as_dtype).reshape(-1))
-            return t.to(self.device)
+            flat = np.ascontiguousarray(arr).view(as_dtype).reshape(-1)
+            if flat.size == 0:
+                return torch.zeros(4, dtype=torch.from_numpy(flat).dtype, device=self.device)
+            return torch.from_numpy(flat).to(self.device)
 
-        self._chunks = up(hp.chunks, np.int16)
-        self._row_ptr = up(hp.row_ptr, np.int32)
-        self._tasks = up(hp.tasks, np.int32)
-        self._w_present = up(hp.w_present, np.int32)
-        self._w_absent = up(hp.w_absent, np.int32)
+        self._buffers = {
+            "chunks": up(hp.chunks, np.int16), "tasks": up(hp.tasks, np.int32),
+            "sorted_idx": up(hp.sorted_idx, np.int16), "sorted_ptr": up(hp.sorted_ptr, np.int32),
+            "bits": up(hp.bits, np.int32),
+            "colsum": up(hp.colsum, np.int32), "w_present": up(hp.w_present, np.int32),
+            "w_absent": up(hp.w_absent, np.int32)}
+        ptr = {k: v.data_ptr() for k, v in self._buffers.items()}
         self.c_plan = _native.PgxPlan(
-            d_chunks=self._chunks.data_ptr() if hp.n_chunks else None,
-            d_row_ptr=self._row_ptr.data_ptr(),
-            d_tasks=self._tasks.data_ptr() if hp.n_tasks else None,
-            d_w_present=self._w_present.data_ptr(),
-            d_w_absent=self._w_absent.data_ptr(),
+            d_chunks=ptr["chunks"], d_tasks=ptr["tasks"], d_sorted_idx=ptr["sorted_idx"],
+            d_sorted_ptr=ptr["sorted_ptr"], d_bits=ptr["bits"], reserved_ptr=None,
+            d_colsum=ptr["colsum"], d_w_present=ptr["w_present"], d_w_absent=ptr["w_absent"],
             n_chunks=hp.n_chunks, n_genomes=hp.n_genomes, n_genes=hp.n_genes,
-            n_rows=hp.n_rows, n_tasks=hp.n_tasks, n_empty=hp.n_empty, n_full=hp.n_full,
-            sum_w_present=int(hp.w_present.sum()), sum_w_absent=int(hp.w_absent.sum()))
+            n_rows=hp.n_rows, n_tasks=hp.n_tasks, n_long=hp.n_long,
+            n_superblocks=hp.n_superblocks, perms_per_cta=hp.perms_per_cta, reserved=0)
 
     # ---- device-resident path -------------------------------------------------------
     def curves_device(self, perms, out=None):

@@ -87,12 +87,14 @@ def _mixed_matrix(n, seed=5, per_class=24):
 
 @pytest.mark.parametrize("perms_per_cta", [1, 2, 4, 8])
 @pytest.mark.parametrize("splits,threads", [(1, 64), (3, 256), (7, 1024)])
-def test_every_launch_shape_and_lane_class(engine_mod, perms_per_cta, splits, threads):
+@pytest.mark.parametrize("threshold", [0, 40])
+def test_every_launch_shape_and_row_kind(engine_mod, perms_per_cta, splits, threads, threshold):
     from pangenomix_b200 import _native
     coo = _mixed_matrix(700)
-    eng = engine_mod.PanCoreEngine(coo)
-    lanes = sorted({(int(m) >> 1) & 7 for m in eng.host_plan.tasks[:, 1]})
-    assert lanes == [0, 1, 2, 3, 4, 5]
+    eng = engine_mod.PanCoreEngine(coo, long_threshold=threshold)
+    hp = eng.host_plan
+    assert (hp.n_long > 0) == (threshold > 0) and hp.n_rows > 0
+    assert len({int(m) & 0xFFFF for m in hp.tasks[:, 1]}) >= 5          # many chunk-count classes
     perms = draw_perms(3, 700, 13).astype(np.uint16)       # 13: not a multiple of any batch
     want = _oracle_curves(coo, perms)
     _native.set_tuning(perms_per_cta, splits, threads)
@@ -102,13 +104,30 @@ def test_every_launch_shape_and_lane_class(engine_mod, perms_per_cta, splits, th
         _native.set_tuning(0, 0, 0)
 
 
-@pytest.mark.parametrize("n", [14000, 20000, 40000, 65535])
+@pytest.mark.parametrize("threshold", [2, 8, 64, 200])
+def test_bitmap_probe_rows(engine_mod, threshold):
+    """Every general gene at or above the threshold goes through the bit-sliced probe kernel:
+    several superblocks (the last one partial), walks of very different lengths."""
+    coo = _mixed_matrix(1500, seed=threshold, per_class=300 if threshold == 8 else 10)
+    eng = engine_mod.PanCoreEngine(coo, long_threshold=threshold)
+    hp = eng.host_plan
+    assert hp.n_long > 0 and (threshold > 2 or hp.n_rows == 0)
+    assert hp.n_superblocks == (hp.n_long + 1023) // 1024
+    perms = draw_perms(17, 1500, 150).astype(np.uint16)
+    assert np.array_equal(eng.curves_host(perms), _oracle_curves(coo, perms))
+
+
+@pytest.mark.parametrize("n", [14000, 20000, 40000, 65503])
 def test_wide_tables_fall_back_to_smaller_batches(engine_mod, n):
-    """N above ~14.5k no longer fits 8 rank tables in shared memory: 4, 2, then 1 per CTA."""
+    """N above ~14k no longer fits 8 rank tables in shared memory: 4, 2, then 1 per CTA."""
     coo = _mixed_matrix(n, seed=n, per_class=6)
     eng = engine_mod.PanCoreEngine(coo)
+    assert eng.host_plan.perms_per_cta == {14000: 8, 20000: 4, 40000: 2, 65503: 1}[n]
+    assert eng.host_plan.n_long > 0
     perms = draw_perms(11, n, 5).astype(np.uint16)
     assert np.array_equal(eng.curves_host(perms), _oracle_curves(coo, perms))
+    lists_only = engine_mod.PanCoreEngine(coo, long_threshold=0)
+    assert np.array_equal(lists_only.curves_host(perms[:2]), _oracle_curves(coo, perms[:2]))
 
 
 def test_degenerate_shapes(engine_mod):

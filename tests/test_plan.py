@@ -6,7 +6,7 @@ import scipy.sparse
 
 from conftest import CURVE_CASES, draw_perms, golden_matrix, load_golden
 from pangenomix_b200.plan import build_host_plan
-from plan_emulator import curves_from_plan
+from plan_emulator import check_layout, curves_from_plan
 
 
 @pytest.mark.parametrize("name", CURVE_CASES)
@@ -26,8 +26,11 @@ def test_plan_accounts_for_every_gene():
     hp = build_host_plan(coo)
     assert hp.n_empty >= 10 and hp.n_full >= 10
     assert hp.w_present.sum() >= 20 and hp.w_absent.sum() >= 20
-    assert hp.n_rows + hp.n_empty + hp.n_full + hp.w_present.sum() + hp.w_absent.sum() == 500
-    assert hp.chunks.shape[0] % 8 == 0 and hp.chunks.dtype == np.uint16
+    assert hp.n_rows + hp.n_long + hp.n_empty + hp.n_full + hp.w_present.sum() + hp.w_absent.sum() == 500
+    assert hp.n_long > 0 and hp.long_threshold == 8
+    assert hp.chunks.shape[0] % (8 * 32) == 0 and hp.chunks.dtype == np.uint16
+    assert np.array_equal(hp.colsum, np.asarray(coo.tocsr().sum(axis=0)).ravel())
+    check_layout(hp)
     assert hp.algorithmic_bytes_per_perm == 4 * coo.nnz + 4 * 501
     assert np.all(hp.row_len <= 37 // 2)
 
@@ -43,15 +46,34 @@ def test_plan_rejects_non_binary_and_oversize():
     assert build_host_plan(z).nnz == 2
 
 
-def test_plan_long_rows_and_all_lane_classes():
-    rng = np.random.RandomState(5)
+def _mixed_matrix(n, seed=5, per_class=40):
+    rng = np.random.RandomState(seed)
+    dens = np.concatenate([np.full(per_class, d) for d in (0.004, 0.015, 0.03, 0.06, 0.12, 0.3, 0.5, 0.8, 0.97)])
+    return (rng.random_sample((dens.size, n)) < dens[:, None]).astype(np.int64)
+
+
+@pytest.mark.parametrize("threshold,perms_per_cta", [(0, 8), (24, 8), (64, 4), (2, 2), (100, 1)])
+def test_plan_list_and_bitmap_rows(threshold, perms_per_cta):
     n = 700
-    dens = np.concatenate([np.full(40, d) for d in (0.004, 0.015, 0.03, 0.06, 0.12, 0.3, 0.5, 0.8, 0.97)])
-    x = (rng.random_sample((dens.size, n)) < dens[:, None]).astype(np.int64)
-    hp = build_host_plan(scipy.sparse.coo_matrix(x))
-    lanes = sorted({(int(m) >> 1) & 7 for m in hp.tasks[:, 1]})
-    assert lanes == [0, 1, 2, 3, 4, 5]
+    x = _mixed_matrix(n)
+    hp = build_host_plan(scipy.sparse.coo_matrix(x), long_threshold=threshold, perms_per_cta=perms_per_cta)
+    if threshold == 0:
+        assert hp.n_long == 0
+    else:
+        assert hp.n_long > 0 and np.all(hp.row_len < threshold)
+        assert hp.bits.shape[0] == hp.n_superblocks * n * 32
+    if threshold == 2:
+        assert hp.n_rows == 0
+    wavefronts = check_layout(hp)
+    # random order gives ~2.5 (8 lanes per wavefront) .. ~3.5 (32 lanes per wavefront)
+    assert (1.0 <= wavefronts < (1.8 if perms_per_cta >= 4 else 2.6)) or hp.n_rows == 0
     perms = draw_perms(3, n, 4)
     import oracle
     pan, core = oracle.pan_core_curves_minrank(scipy.sparse.coo_matrix(x), perms)
     assert np.array_equal(curves_from_plan(hp, perms), np.hstack([pan, core]).astype(np.int64))
+
+
+def test_plan_bank_order_beats_sorted_order():
+    x = _mixed_matrix(4000, seed=9, per_class=64)
+    hp = build_host_plan(scipy.sparse.coo_matrix(x), long_threshold=0, perms_per_cta=8)
+    assert check_layout(hp) < 1.6
