@@ -48,9 +48,10 @@ enum {
  *                per-genome vectors d_colsum / d_w_present / d_w_absent.
  *  list rows     Every other gene whose SHORTER list (present genomes or absent genomes) has
  *                fewer than the plan's long threshold entries stores that list as uint16
- *                genome indices in 16-byte chunks.  A warp task is up to 32 rows with the
+ *                genome indices in 16-byte chunks.  A sub-block is up to 32 rows with the
  *                same chunk count and list kind, one lane per row; lane l reads chunk
- *                first_chunk + it * 32 + l at iteration it.  Unused slots hold sentinel
+ *                first_chunk + it * 32 + l at iteration it; a warp task streams a run of
+ *                consecutive sub-blocks.  Unused slots hold sentinel
  *                indices in [N, N + 32) whose rank-table entry is 0xffff.  Entries are
  *                ordered inside a row so that neighbouring lanes gather from different
  *                shared-memory banks.  d_sorted_* hold the same lists plainly sorted.
@@ -61,8 +62,9 @@ enum {
  */
 typedef struct pgx_plan {
     const uint16_t *d_chunks;      /* [n_chunks * 8] list rows, 16-byte aligned */
-    const int32_t *d_tasks;        /* [n_tasks * 4] {first_chunk, chunks_per_row | rows << 16 | absent_list << 24,
-                                      first_row, 0}, 16-byte aligned, costly tasks first */
+    const int32_t *d_tasks;        /* [n_tasks * 4] {first_chunk, chunks_per_row | absent_list << 24, first_row,
+                                      rows}: a run of ceil(rows / 32) consecutive sub-blocks; 16-byte aligned,
+                                      costly tasks first */
     const uint16_t *d_sorted_idx;  /* sorted copy of the list rows */
     const int32_t *d_sorted_ptr;   /* [n_rows + 1] offsets into d_sorted_idx */
     const uint32_t *d_bits;        /* [n_superblocks * n_genomes * 32] bit-sliced bitmap rows, 16-byte aligned */

@@ -13,6 +13,7 @@ REPO = os.path.dirname(HERE)
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpgx_b200.so")
 SOURCES = ["pgx_api.cu", "pgx_rarefy.cu", "pgx_bernoulli.cu"]
+HOST_SOURCES = ["pgx_rng.cpp"]            # plain C++ (g++): AVX2 paths are selected at run time
 HEADERS = [os.path.join(CSRC, "pgx_common.cuh"), os.path.join(REPO, "include", "pgx.h")]
 
 
@@ -27,19 +28,25 @@ def needs_build():
     if not os.path.exists(LIB):
         return True
     built = os.path.getmtime(LIB)
-    deps = [os.path.join(CSRC, s) for s in SOURCES] + HEADERS
+    deps = [os.path.join(CSRC, s) for s in SOURCES + HOST_SOURCES] + HEADERS
     return any(os.path.getmtime(d) > built for d in deps)
 
 
 def build(force=False, verbose=False):
     if not force and not needs_build():
         return LIB
+    objects = []
+    for src in HOST_SOURCES:
+        obj = os.path.join(CSRC, os.path.splitext(src)[0] + ".o")
+        subprocess.run([os.environ.get("CXX", "g++"), "-O3", "-std=c++17", "-fPIC", "-pthread",
+                        "-I", os.path.join(REPO, "include"), "-c", os.path.join(CSRC, src), "-o", obj], check=True)
+        objects.append(obj)
     cmd = [nvcc_path(), "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a",
-           "-lineinfo", "-Xcompiler", "-fPIC,-O3", "-shared",
+           "-lineinfo", "-Xcompiler", "-fPIC,-O3,-pthread", "-shared",
            "-I", os.path.join(REPO, "include"), "-I", CSRC, "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]
-    cmd += [os.path.join(CSRC, s) for s in SOURCES]
+    cmd += [os.path.join(CSRC, s) for s in SOURCES] + objects
     subprocess.run(cmd, check=True)
     return LIB
 

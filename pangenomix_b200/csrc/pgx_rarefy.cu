@@ -24,6 +24,8 @@
 //   genome's bit is the gene's statistic.  O(N / m) steps instead of O(m) gathers.
 // Kernel 3 (scan_kernel): adds the closed-form gene classes and turns each histogram into
 //   its curve with a block-wide prefix scan, in place.
+#include <stdlib.h>
+
 #include <mutex>
 #include <vector>
 
@@ -46,6 +48,7 @@ struct Tuning {
     int threads = 0;
 };
 Tuning g_tuning;
+const bool g_no_overlap = getenv("PGX_NO_OVERLAP") != nullptr;
 
 template <int B>
 struct Packed {
@@ -109,11 +112,15 @@ __device__ __noinline__ int mex_probe(const uint16_t *__restrict__ perm,
 
 // Deferred mex events of a warp: (list row << 4 | absent_list << 3 | permutation slot).
 constexpr int EVENT_QUEUE = 64;
+constexpr int LIST_DEPTH = 4;           // chunk loads in flight per lane
 
+// 48 registers x 1,024 threads leave a quarter of the register file to the probe kernel's CTAs,
+// which run beside this one on a second stream (the list kernel is bound by the shared-memory
+// pipe, the probe kernel by instruction issue).
 template <int B>
-__global__ void __launch_bounds__(1024, 1)
+__global__ void __maxnreg__(48)
 list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long long n_perm,
-            int32_t *__restrict__ hist)
+            int32_t *__restrict__ hist, const int splits, const long long n_items)
 {
     extern __shared__ __align__(16) uint16_t table[];   // [(N + 32)][B], then the warps' event queues
     __shared__ int s_next_task;
@@ -122,34 +129,38 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
     const int n = plan.n_genomes;
     const int tid = threadIdx.x;
     const int lane = tid & 31;
-    const long long p0 = static_cast<long long>(blockIdx.y) * B;
-    const int n_valid = static_cast<int>(min(static_cast<long long>(B), n_perm - p0));
     uint32_t *queue = reinterpret_cast<uint32_t *>(table + ((static_cast<size_t>(n + SENTINELS) * B + 7) & ~size_t(7))) +
                       (tid >> 5) * EVENT_QUEUE;
+    const uint4 *__restrict__ chunks = reinterpret_cast<const uint4 *>(plan.d_chunks);
+    const int4 *__restrict__ tasks = reinterpret_cast<const int4 *>(plan.d_tasks);
+    const long long row_stride = 2ll * n;
 
-    // ---- stage the inverse permutations: T[perm[k]][q] = k ----
-    for (int q = 0; q < B; ++q) {
-        if (q < n_valid) {
-            const uint16_t *perm = perms + (p0 + q) * n;
-            for (int k = tid; k < n; k += blockDim.x) table[static_cast<uint32_t>(perm[k]) * B + q] = static_cast<uint16_t>(k);
-        } else {
-            for (int k = tid; k < n; k += blockDim.x) table[k * B + q] = 0xffffu;
-        }
+    // Persistent CTAs: item = (batch of B permutations, share ``split`` of the tasks).  The whole
+    // grid is resident at once, so CTAs of the probe kernel can fill the rest of every SM.
+    for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
+    const long long p0 = (item / splits) * B;
+    const int split = static_cast<int>(item % splits);
+    const int n_valid = static_cast<int>(min(static_cast<long long>(B), n_perm - p0));
+
+    // ---- stage the inverse permutations: T[perm[k]][q] = k (B independent loads in flight) ----
+    for (int k = tid; k < n; k += blockDim.x) {
+        uint32_t g[B];
+#pragma unroll
+        for (int q = 0; q < B; ++q) g[q] = q < n_valid ? perms[(p0 + q) * n + k] : static_cast<uint32_t>(k);
+#pragma unroll
+        for (int q = 0; q < B; ++q) table[g[q] * B + q] = q < n_valid ? static_cast<uint16_t>(k) : static_cast<uint16_t>(0xffffu);
     }
     for (int k = tid; k < SENTINELS * B; k += blockDim.x) table[n * B + k] = 0xffffu;   // never win a min
     if (tid == 0) s_next_task = 0;
     __syncthreads();
 
-    const uint4 *__restrict__ chunks = reinterpret_cast<const uint4 *>(plan.d_chunks);
-    const int4 *__restrict__ tasks = reinterpret_cast<const int4 *>(plan.d_tasks);
-    const long long row_stride = 2ll * n;
     int queued = 0;                                       // warp-uniform
 
     auto next_task = [&]() -> int4 {
         int t = 0;
         if (lane == 0) t = atomicAdd(&s_next_task, 1);
         t = __shfl_sync(FULL_MASK, t, 0);
-        const long long task = static_cast<long long>(t) * gridDim.x + blockIdx.x;
+        const long long task = static_cast<long long>(t) * splits + split;
         return task < plan.n_tasks ? __ldg(tasks + task) : make_int4(0, 0, 0, 0);
     };
     // mex of one queued (row, permutation): all lanes of the warp work on different events
@@ -161,63 +172,73 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
         if (k < n) atomicAdd(hist + (p0 + q) * row_stride + ((ev & 8) ? 0 : n) + k, 1);
     };
 
-    // Two tasks ahead: descriptor of task i+2 and first chunk of task i+1 are in flight
-    // while task i is gathered.
+    // A task is a run of consecutive sub-blocks (32 rows x nch chunks each) laid out back to
+    // back, so the warp streams chunk iterations 0 .. n_sub * nch - 1 with LIST_DEPTH loads in
+    // flight and closes a sub-block every nch iterations.  The next task's descriptor is
+    // fetched while the current one streams.
     int4 td = next_task();
-    int4 td_next = next_task();
-    uint4 cur = make_uint4(0, 0, 0, 0);
-    if (td.y & 0xffff) cur = ldg_stream(chunks + td.x + lane);
     while (td.y & 0xffff) {
-        const int4 td_after = next_task();
-        uint4 first_next = make_uint4(0, 0, 0, 0);
-        if (td_next.y & 0xffff) first_next = ldg_stream(chunks + td_next.x + lane);
-
+        const int4 td_next = next_task();
         const int nch = td.y & 0xffff;
-        const int n_rows = (td.y >> 16) & 0xff;
         const uint32_t absent_list = (td.y >> 24) & 1;
+        const int n_rows = td.w;
+        const int total = ((n_rows + 31) >> 5) * nch;
         const uint4 *cp = chunks + td.x + lane;
+        int32_t *list_hist = hist + (absent_list ? n : 0);
+
+        uint4 buf[LIST_DEPTH];
+#pragma unroll
+        for (int d = 0; d < LIST_DEPTH; ++d) buf[d] = d < total ? ldg_stream(cp + d * 32) : make_uint4(0, 0, 0, 0);
 
         uint32_t acc[REGS];
 #pragma unroll
         for (int i = 0; i < REGS; ++i) acc[i] = 0xffffffffu;
-        for (int it = 1; it < nch; ++it) {
-            const uint4 nxt = ldg_stream(cp + it * 32);
-            gather_chunk<B>(table, cur, acc);
-            cur = nxt;
-        }
-        gather_chunk<B>(table, cur, acc);
-
-        const bool valid = lane < n_rows;
-        int32_t *list_hist = hist + (absent_list ? n : 0);
+        int left = nch, row = td.z + lane, rows_left = n_rows - lane;
+        for (int s = 0; s < total; ++s) {
+            const uint4 cur = buf[0];
 #pragma unroll
-        for (int q = 0; q < B; ++q) {
-            if (q < n_valid) {
-                uint32_t mn;
-                if constexpr (B == 1) mn = acc[0] & 0xffffu;
-                else mn = (acc[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
-                if (valid && mn != 0) atomicAdd(list_hist + (p0 + q) * row_stride + mn, 1);
-                // min == 0: the wanted statistic is the mex; queue it, resolve 32 at a time
-                const bool ev = valid && mn == 0;
-                const uint32_t m = __ballot_sync(FULL_MASK, ev);
-                if (m) {
-                    if (ev) queue[queued + __popc(m & ((1u << lane) - 1u))] =
-                        (static_cast<uint32_t>(td.z + lane) << 4) | (absent_list << 3) | q;
-                    queued += __popc(m);
-                    __syncwarp();
-                    if (queued >= 32) {
-                        queued -= 32;
-                        const uint32_t e = queue[queued + lane];
+            for (int d = 0; d + 1 < LIST_DEPTH; ++d) buf[d] = buf[d + 1];
+            if (s + LIST_DEPTH < total) buf[LIST_DEPTH - 1] = ldg_stream(cp + (s + LIST_DEPTH) * 32);
+            gather_chunk<B>(table, cur, acc);
+            if (--left) continue;
+
+            // ---- a sub-block is complete: one statistic per (row, permutation) ----
+            const bool valid = rows_left > 0;
+#pragma unroll
+            for (int q = 0; q < B; ++q) {
+                if (q < n_valid) {
+                    uint32_t mn;
+                    if constexpr (B == 1) mn = acc[0] & 0xffffu;
+                    else mn = (acc[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
+                    if (valid && mn != 0) atomicAdd(list_hist + (p0 + q) * row_stride + mn, 1);
+                    // min == 0: the wanted statistic is the mex; queue it, resolve 32 at a time
+                    const bool ev = valid && mn == 0;
+                    const uint32_t m = __ballot_sync(FULL_MASK, ev);
+                    if (m) {
+                        if (ev) queue[queued + __popc(m & ((1u << lane) - 1u))] =
+                            (static_cast<uint32_t>(row) << 4) | (absent_list << 3) | q;
+                        queued += __popc(m);
                         __syncwarp();
-                        resolve(e);
+                        if (queued >= 32) {
+                            queued -= 32;
+                            const uint32_t e = queue[queued + lane];
+                            __syncwarp();
+                            resolve(e);
+                        }
                     }
                 }
             }
+#pragma unroll
+            for (int i = 0; i < REGS; ++i) acc[i] = 0xffffffffu;
+            left = nch;
+            row += 32;
+            rows_left -= 32;
         }
         td = td_next;
-        cur = first_next;
-        td_next = td_after;
     }
     if (lane < queued) resolve(queue[lane]);
+    __syncthreads();                                      // every warp is done with this table
+    }
 }
 
 // Bitmap rows, bit-sliced: 32 genes per word, genome-major.  A warp owns one superblock of
@@ -251,26 +272,31 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
     uint32_t pending = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
     const uint32_t b0 = __ldg(lines + static_cast<size_t>(perm[0]) * 32);
 
+    const uint32_t genome0 = perm[0];
     for (int k0 = 0; k0 < n; k0 += 32) {
-        const uint32_t chunk = k0 + lane < n ? perm[k0 + lane] : 0u;      // genomes of ranks k0 .. k0 + 31
+        // genomes of ranks k0 .. k0 + 31; ranks past the end repeat the rank-0 genome (never a flip)
+        const uint32_t chunk = k0 + lane < n ? perm[k0 + lane] : genome0;
 #pragma unroll 1
         for (int j0 = 0; j0 < 32; j0 += SLICE_DEPTH) {
-            uint32_t w[SLICE_DEPTH];
+            uint32_t d[SLICE_DEPTH];
+            uint32_t any = 0;
 #pragma unroll
             for (int j = 0; j < SLICE_DEPTH; ++j) {
                 const uint32_t c = __shfl_sync(FULL_MASK, chunk, j0 + j);
-                w[j] = __ldg(lines + static_cast<size_t>(c) * 32);
+                d[j] = __ldg(lines + static_cast<size_t>(c) * 32) ^ b0;
+                any |= d[j];
             }
+            // late in the walk few genes are pending and most groups of 8 genomes flip none
+            if (!__any_sync(FULL_MASK, any & pending)) continue;
 #pragma unroll
             for (int j = 0; j < SLICE_DEPTH; ++j) {
-                const int k = k0 + j0 + j;
-                const uint32_t flipped = k < n ? (w[j] ^ b0) & pending : 0u;
+                const uint32_t flipped = d[j] & pending;
                 pending &= ~flipped;
                 // low half: genes first seen at k (pan side); high half: genes first missed at k (core side)
                 const uint32_t packed = __popc(flipped & ~b0) | (__popc(flipped & b0) << 16);
                 const uint32_t total = __reduce_add_sync(FULL_MASK, packed);
                 const uint32_t mine = lane == 1 ? total >> 16 : total & 0xffffu;
-                if (lane < 2 && mine) atomicAdd(out + k, static_cast<int>(mine));
+                if (lane < 2 && mine) atomicAdd(out + (k0 + j0 + j), static_cast<int>(mine));
             }
             if (!__any_sync(FULL_MASK, pending)) return;
         }
@@ -412,16 +438,12 @@ int launch_list(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm,
         splits = static_cast<int>(max(1ll, min(want, most)));
     }
     splits = max(1, min(splits, 65535));
-    if (batches > 65535ll * 32768ll) return fail(PGX_ERR_UNSUPPORTED, "too many permutations in one call");
-    // blockIdx.y is limited to 65535: fold the batch index when needed.
-    for (long long b0 = 0; b0 < batches; b0 += 65535) {
-        const long long nb = min(65535ll, batches - b0);
-        dim3 grid(static_cast<unsigned>(splits), static_cast<unsigned>(nb));
-        list_kernel<B><<<grid, threads, smem, stream>>>(plan, d_perms + b0 * B * plan.n_genomes,
-                                                         n_perm - b0 * B,
-                                                         d_hist + b0 * B * 2ll * plan.n_genomes);
-        PGX_LAUNCH_CHECK("list_kernel");
-    }
+    const long long n_items = batches * splits;
+    int per_sm = 1;
+    PGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, list_kernel<B>, threads, smem));
+    const long long grid = max(1ll, min(n_items, static_cast<long long>(lim.sm_count) * max(1, per_sm)));
+    list_kernel<B><<<static_cast<unsigned>(grid), threads, smem, stream>>>(plan, d_perms, n_perm, d_hist, splits, n_items);
+    PGX_LAUNCH_CHECK("list_kernel");
     return PGX_OK;
 }
 
@@ -434,6 +456,30 @@ int launch_probe(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm
     if (blocks > 2147483647ll) return fail(PGX_ERR_UNSUPPORTED, "too many (superblock, permutation) units in one call");
     probe_kernel<<<static_cast<unsigned>(blocks), SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, d_hist);
     PGX_LAUNCH_CHECK("probe_kernel");
+    return PGX_OK;
+}
+
+// Second stream + fork/join events of the calling thread's current device.
+struct Aux {
+    int device = -1;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t fork = nullptr, join = nullptr;
+};
+
+int aux_for_device(Aux **out)
+{
+    static thread_local Aux aux[64];
+    int dev = 0;
+    PGX_CUDA(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(PGX_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
+    Aux &a = aux[dev];
+    if (a.device != dev) {
+        PGX_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+        PGX_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+        PGX_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+        a.device = dev;
+    }
+    *out = &a;
     return PGX_OK;
 }
 
@@ -458,6 +504,15 @@ int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, 
         PGX_CUDA(cudaEventCreate(&ev.end));
         PGX_CUDA(cudaEventRecord(ev.begin, stream));
     }
+    // The two row kernels only add into the histogram, in any order: unless per-kernel timing is
+    // on (or PGX_NO_OVERLAP is set), the probe kernel runs beside the list kernel on a second stream.
+    Aux *aux = nullptr;
+    const bool overlap = !profile && !g_no_overlap && plan->n_tasks > 0 && plan->n_long > 0;
+    if (overlap) {
+        if (int rc = aux_for_device(&aux)) return rc;
+        PGX_CUDA(cudaEventRecord(aux->fork, stream));
+        PGX_CUDA(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
+    }
     if (plan->n_tasks > 0) {
         const size_t per_perm = static_cast<size_t>(n + SENTINELS) * sizeof(uint16_t);
         const size_t budget = static_cast<size_t>(lim.smem_optin) - 64 - 32 * EVENT_QUEUE * sizeof(uint32_t);
@@ -476,7 +531,12 @@ int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, 
         if (rc) return rc;
     }
     if (profile) PGX_CUDA(cudaEventRecord(ev.list_done, stream));
-    if (plan->n_long > 0) {
+    if (overlap) {
+        // launched AFTER the list kernel: one list CTA per SM first, probe CTAs fill what is left
+        if (int rc = launch_probe(*plan, d_perms, n_perm, d_hist, aux->stream)) return rc;
+        PGX_CUDA(cudaEventRecord(aux->join, aux->stream));
+        PGX_CUDA(cudaStreamWaitEvent(stream, aux->join, 0));
+    } else if (plan->n_long > 0) {
         if (int rc = launch_probe(*plan, d_perms, n_perm, d_hist, stream)) return rc;
     }
     if (profile) PGX_CUDA(cudaEventRecord(ev.probe_done, stream));

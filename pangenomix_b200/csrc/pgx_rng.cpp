@@ -1,0 +1,382 @@
+// Host-side numpy-legacy permutation stream of libpgx_b200 (plain C++, no CUDA).
+//
+// Replaces the pair ``shuffle_indices = np.arange(N); np.random.shuffle(shuffle_indices)`` of
+// /root/reference/pangenomix/pangenome_analysis.py:84-85 for the legacy global RandomState:
+// MT19937 (Matsumoto & Nishimura) + Fisher-Yates from the top, j in [0, i] by masked
+// rejection on successive 32-bit outputs (mask = smallest 2^b - 1 >= i), bit-exactly.
+//
+// The stream is serial, but only two of its three stages are: (1) generating raw MT19937
+// words and (2) deciding which words are accepted (that decides where the next shuffle
+// starts).  Both are vectorised here (AVX2 when the CPU has it).  Stage (3), applying the
+// accepted swap targets to the identity permutation, is independent per shuffle and runs
+// on worker threads, two shuffles interleaved per thread for instruction-level parallelism.
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <deque>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define PGX_X86 1
+#else
+#define PGX_X86 0
+#endif
+
+#include "pgx.h"
+
+namespace pgx {
+int fail(int code, const char *fmt, ...);
+}
+
+namespace {
+
+constexpr uint32_t MT_UPPER = 0x80000000u, MT_LOWER = 0x7fffffffu, MT_MAGIC = 0x9908b0dfu;
+
+// ``pos`` counts the words of the current block already consumed (624 = block exhausted),
+// exactly as np.random.get_state() reports it.
+struct Mt19937 {
+    alignas(64) uint32_t key[624 + 8];
+    alignas(64) uint32_t out[624 + 8];
+    int pos;
+    bool avx2;
+
+    static inline uint32_t twist(uint32_t a, uint32_t b, uint32_t far)
+    {
+        const uint32_t y = (a & MT_UPPER) | (b & MT_LOWER);
+        return far ^ (y >> 1) ^ (-(y & 1u) & MT_MAGIC);
+    }
+
+    static inline uint32_t temper1(uint32_t y)
+    {
+        y ^= y >> 11;
+        y ^= (y << 7) & 0x9d2c5680u;
+        y ^= (y << 15) & 0xefc60000u;
+        y ^= y >> 18;
+        return y;
+    }
+
+    void temper_scalar()
+    {
+        for (int k = 0; k < 624; ++k) out[k] = temper1(key[k]);
+    }
+
+    void refill_scalar()
+    {
+        int k = 0;
+        for (; k < 624 - 397; ++k) key[k] = twist(key[k], key[k + 1], key[k + 397]);
+        for (; k < 623; ++k) key[k] = twist(key[k], key[k + 1], key[k + (397 - 624)]);
+        key[623] = twist(key[623], key[0], key[396]);
+        temper_scalar();
+    }
+
+#if PGX_X86
+    __attribute__((target("avx2"))) static inline __m256i twist8(__m256i a, __m256i b, __m256i far)
+    {
+        const __m256i y = _mm256_or_si256(_mm256_and_si256(a, _mm256_set1_epi32(static_cast<int>(MT_UPPER))),
+                                          _mm256_and_si256(b, _mm256_set1_epi32(static_cast<int>(MT_LOWER))));
+        const __m256i odd = _mm256_sub_epi32(_mm256_setzero_si256(), _mm256_and_si256(y, _mm256_set1_epi32(1)));
+        return _mm256_xor_si256(_mm256_xor_si256(far, _mm256_srli_epi32(y, 1)),
+                                _mm256_and_si256(odd, _mm256_set1_epi32(static_cast<int>(MT_MAGIC))));
+    }
+
+    __attribute__((target("avx2"))) void refill_avx2()
+    {
+        // key[k] for k < 227 needs OLD key[k + 1], key[k + 397]: reads run ahead of writes.
+        int k = 0;
+        for (; k + 8 <= 227; k += 8) {
+            const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(key + k));
+            const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(key + k + 1));
+            const __m256i f = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(key + k + 397));
+            _mm256_storeu_si256(reinterpret_cast<__m256i *>(key + k), twist8(a, b, f));
+        }
+        for (; k < 227; ++k) key[k] = twist(key[k], key[k + 1], key[k + 397]);
+        // 227 <= k < 623 needs NEW key[k - 227] (written >= 227 steps ago) and OLD key[k + 1]
+        for (; k + 8 <= 623; k += 8) {
+            const __m256i a = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(key + k));
+            const __m256i b = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(key + k + 1));
+            const __m256i f = _mm256_loadu_si256(reinterpret_cast<const __m256i *>(key + k - 227));
+            _mm256_storeu_si256(reinterpret_cast<__m256i *>(key + k), twist8(a, b, f));
+        }
+        for (; k < 623; ++k) key[k] = twist(key[k], key[k + 1], key[k - 227]);
+        key[623] = twist(key[623], key[0], key[396]);
+        for (k = 0; k < 624; k += 8) {
+            __m256i y = _mm256_load_si256(reinterpret_cast<const __m256i *>(key + k));
+            y = _mm256_xor_si256(y, _mm256_srli_epi32(y, 11));
+            y = _mm256_xor_si256(y, _mm256_and_si256(_mm256_slli_epi32(y, 7), _mm256_set1_epi32(static_cast<int>(0x9d2c5680u))));
+            y = _mm256_xor_si256(y, _mm256_and_si256(_mm256_slli_epi32(y, 15), _mm256_set1_epi32(static_cast<int>(0xefc60000u))));
+            y = _mm256_xor_si256(y, _mm256_srli_epi32(y, 18));
+            _mm256_store_si256(reinterpret_cast<__m256i *>(out + k), y);
+        }
+    }
+#endif
+
+    void refill()
+    {
+#if PGX_X86
+        if (avx2) {
+            refill_avx2();
+            pos = 0;
+            return;
+        }
+#endif
+        refill_scalar();
+        pos = 0;
+    }
+};
+
+// Compress table for AVX2: lane permutation that packs the lanes selected by an 8-bit mask.
+struct CompressLut {
+    alignas(32) uint32_t idx[256][8];
+    CompressLut()
+    {
+        for (int m = 0; m < 256; ++m) {
+            int w = 0;
+            for (int l = 0; l < 8; ++l)
+                if (m & (1 << l)) idx[m][w++] = l;
+            for (; w < 8; ++w) idx[m][w] = 0;
+        }
+    }
+};
+const CompressLut g_lut;
+
+// Stage 2: the accepted swap targets of ONE shuffle of n elements: js[t] = j drawn for
+// i = n - 1 - t.  js must have room for n - 1 + 8 entries (vector stores overrun).
+void accept_scalar_span(Mt19937 &mt, uint32_t &i, uint32_t lo, uint32_t mask, uint32_t *&w)
+{
+    while (i >= lo) {
+        if (mt.pos >= 624) mt.refill();
+        const uint32_t *src = mt.out + mt.pos;
+        const int avail = 624 - mt.pos;
+        int t = 0;
+        for (; t < avail && i >= lo; ++t) {
+            const uint32_t v = src[t] & mask;
+            const uint32_t ok = v <= i;
+            *w = v;
+            w += ok;
+            i -= ok;
+        }
+        mt.pos += t;
+    }
+}
+
+#if PGX_X86
+__attribute__((target("avx2,popcnt")))
+void accept_avx2_span(Mt19937 &mt, uint32_t &i_io, uint32_t lo, uint32_t mask, uint32_t *&w_io)
+{
+    uint32_t i = i_io;
+    uint32_t *w = w_io;
+    int pos = mt.pos;
+    const __m256i maskv = _mm256_set1_epi32(static_cast<int>(mask));
+    // all 8 draws of a vector see the same mask as long as i - 7 >= lo even if every one is accepted
+    while (i >= lo + 8) {
+        if (pos + 8 > 624) {
+            if (pos >= 624) { mt.refill(); pos = 0; continue; }
+            break;                                   // block tail: the scalar loop finishes it
+        }
+        const __m256i v = _mm256_and_si256(_mm256_loadu_si256(reinterpret_cast<const __m256i *>(mt.out + pos)), maskv);
+        // lane l is tested against i - (accepts among lanes < l), which lies in [i - 7, i]
+        const __m256i iv = _mm256_set1_epi32(static_cast<int>(i));
+        const __m256i sure = _mm256_cmpgt_epi32(_mm256_sub_epi32(iv, _mm256_set1_epi32(6)), v);      // v <= i - 7
+        const __m256i over = _mm256_cmpgt_epi32(v, iv);                                              // v >  i
+        const int sure_m = _mm256_movemask_ps(_mm256_castsi256_ps(sure));
+        const int both_m = _mm256_movemask_ps(_mm256_castsi256_ps(_mm256_or_si256(sure, over)));
+        if (both_m != 0xff) break;                   // an ambiguous lane: resolve this vector one by one
+        const __m256i packed = _mm256_permutevar8x32_epi32(v, _mm256_load_si256(reinterpret_cast<const __m256i *>(g_lut.idx[sure_m])));
+        _mm256_storeu_si256(reinterpret_cast<__m256i *>(w), packed);
+        const uint32_t got = static_cast<uint32_t>(_mm_popcnt_u32(static_cast<unsigned>(sure_m)));
+        w += got;
+        i -= got;
+        pos += 8;
+    }
+    mt.pos = pos;
+    i_io = i;
+    w_io = w;
+}
+#endif
+
+void accept_one(Mt19937 &mt, uint32_t n, uint32_t *js)
+{
+    if (n < 2) return;
+    uint32_t i = n - 1;
+    uint32_t *w = js;
+    while (i > 0) {
+        const int bits = 32 - __builtin_clz(i);
+        const uint32_t mask = 0xffffffffu >> (32 - bits);          // smallest 2^b - 1 >= i
+        const uint32_t lo = 1u << (bits - 1);                      // the mask holds while i >= lo
+#if PGX_X86
+        if (mt.avx2 && mask < 0x80000000u) {
+            // alternate: vector spans while far from lo and unambiguous, scalar for what is left
+            while (i >= lo) {
+                accept_avx2_span(mt, i, lo, mask, w);
+                if (i < lo) break;
+                // one scalar draw-by-draw stretch of at most 8 draws, then try vectors again
+                uint32_t done = 0;
+                while (i >= lo && done < 8) {
+                    if (mt.pos >= 624) mt.refill();
+                    const uint32_t v = mt.out[mt.pos++] & mask;
+                    const uint32_t ok = v <= i;
+                    *w = v;
+                    w += ok;
+                    i -= ok;
+                    ++done;
+                }
+            }
+            continue;
+        }
+#endif
+        accept_scalar_span(mt, i, lo, mask, w);
+    }
+}
+
+// Stage 3: Fisher-Yates from the top with the accepted targets; two shuffles at a time.
+inline void apply_one(uint32_t n, const uint32_t *js, uint16_t *a)
+{
+    for (uint32_t k = 0; k < n; ++k) a[k] = static_cast<uint16_t>(k);
+    for (uint32_t i = n - 1, t = 0; n > 1 && i > 0; --i, ++t) {
+        const uint32_t j = js[t];
+        const uint16_t ai = a[i], aj = a[j];
+        a[i] = aj;
+        a[j] = ai;
+    }
+}
+
+inline void apply_two(uint32_t n, const uint32_t *js0, uint16_t *a0, const uint32_t *js1, uint16_t *a1)
+{
+    for (uint32_t k = 0; k < n; ++k) a0[k] = a1[k] = static_cast<uint16_t>(k);
+    for (uint32_t i = n - 1, t = 0; n > 1 && i > 0; --i, ++t) {
+        const uint32_t j0 = js0[t], j1 = js1[t];
+        const uint16_t x0 = a0[i], y0 = a0[j0];
+        const uint16_t x1 = a1[i], y1 = a1[j1];
+        a0[i] = y0;
+        a0[j0] = x0;
+        a1[i] = y1;
+        a1[j1] = x1;
+    }
+}
+
+void apply_batch(uint32_t n, size_t stride, const uint32_t *js, uint16_t *perms, int count)
+{
+    int s = 0;
+    for (; s + 2 <= count; s += 2)
+        apply_two(n, js + s * stride, perms + static_cast<size_t>(s) * n, js + (s + 1) * stride,
+                  perms + static_cast<size_t>(s + 1) * n);
+    if (s < count) apply_one(n, js + s * stride, perms + static_cast<size_t>(s) * n);
+}
+
+int worker_threads_wanted()
+{
+    if (const char *env = getenv("PGX_RNG_THREADS")) {
+        const int v = atoi(env);
+        if (v >= 0) return std::min(v, 64);
+    }
+    const unsigned hw = std::thread::hardware_concurrency();
+    return static_cast<int>(std::min(4u, hw > 1 ? hw - 1 : 0u));
+}
+
+}  // namespace
+
+extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n, int64_t count,
+                                   uint16_t *h_perms)
+{
+    if (!mt_key || !mt_pos || (!h_perms && n * count > 0))
+        return pgx::fail(PGX_ERR_INVALID, "null pointer passed to pgx_legacy_shuffles");
+    if (n < 0 || n > 65535) return pgx::fail(PGX_ERR_UNSUPPORTED, "n = %lld outside 0..65535", (long long)n);
+    if (count < 0 || *mt_pos < 0 || *mt_pos > 624) return pgx::fail(PGX_ERR_INVALID, "bad MT19937 position / count");
+
+    static Mt19937 mt_storage;                 // 5 KB; calls are serialised by the caller's RNG ownership anyway
+    static std::mutex call_mu;
+    std::lock_guard<std::mutex> call_lock(call_mu);
+    Mt19937 &mt = mt_storage;
+    memcpy(mt.key, mt_key, sizeof(uint32_t) * 624);
+    mt.pos = *mt_pos;
+#if PGX_X86
+    mt.avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt") && !getenv("PGX_RNG_SCALAR");
+#else
+    mt.avx2 = false;
+#endif
+    mt.temper_scalar();
+
+    const uint32_t un = static_cast<uint32_t>(n);
+    const size_t stride = static_cast<size_t>(n) + 8;          // js row, with room for vector overrun
+    const int batch = static_cast<int>(std::max<int64_t>(2, std::min<int64_t>(64, (1 << 17) / std::max<int64_t>(n, 1))));
+    int workers = (n >= 64 && count >= 4 * batch) ? worker_threads_wanted() : 0;
+
+    if (workers == 0) {
+        std::vector<uint32_t> js(stride * 2);
+        int64_t t = 0;
+        for (; t + 2 <= count; t += 2) {
+            accept_one(mt, un, js.data());
+            accept_one(mt, un, js.data() + stride);
+            apply_two(un, js.data(), h_perms + t * n, js.data() + stride, h_perms + (t + 1) * n);
+        }
+        if (t < count) {
+            accept_one(mt, un, js.data());
+            apply_one(un, js.data(), h_perms + t * n);
+        }
+    } else {
+        // producer (this thread): stages 1-2 into a ring of batch buffers; workers: stage 3
+        struct Slot { std::vector<uint32_t> js; int64_t first = 0; int count = 0; };
+        const int n_slots = 2 * workers + 2;
+        std::vector<Slot> slots(n_slots);
+        for (auto &s : slots) s.js.resize(stride * batch);
+        std::mutex mu;
+        std::condition_variable cv_work, cv_free;
+        std::deque<int> ready, free_slots;
+        for (int s = 0; s < n_slots; ++s) free_slots.push_back(s);
+        bool done = false;
+        std::vector<std::thread> pool;
+        for (int w = 0; w < workers; ++w) {
+            pool.emplace_back([&]() {
+                for (;;) {
+                    int s;
+                    {
+                        std::unique_lock<std::mutex> lock(mu);
+                        cv_work.wait(lock, [&] { return done || !ready.empty(); });
+                        if (ready.empty()) return;
+                        s = ready.front();
+                        ready.pop_front();
+                    }
+                    apply_batch(un, stride, slots[s].js.data(), h_perms + slots[s].first * n, slots[s].count);
+                    {
+                        std::lock_guard<std::mutex> lock(mu);
+                        free_slots.push_back(s);
+                    }
+                    cv_free.notify_one();
+                }
+            });
+        }
+        for (int64_t t = 0; t < count; t += batch) {
+            int s;
+            {
+                std::unique_lock<std::mutex> lock(mu);
+                cv_free.wait(lock, [&] { return !free_slots.empty(); });
+                s = free_slots.front();
+                free_slots.pop_front();
+            }
+            const int c = static_cast<int>(std::min<int64_t>(batch, count - t));
+            for (int b = 0; b < c; ++b) accept_one(mt, un, slots[s].js.data() + b * stride);
+            slots[s].first = t;
+            slots[s].count = c;
+            {
+                std::lock_guard<std::mutex> lock(mu);
+                ready.push_back(s);
+            }
+            cv_work.notify_one();
+        }
+        {
+            std::lock_guard<std::mutex> lock(mu);
+            done = true;
+        }
+        cv_work.notify_all();
+        for (auto &th : pool) th.join();
+    }
+    memcpy(mt_key, mt.key, sizeof(uint32_t) * 624);
+    *mt_pos = mt.pos;
+    return PGX_OK;
+}

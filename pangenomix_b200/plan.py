@@ -12,8 +12,9 @@ Three populations of genes (include/pgx.h describes the device side):
                     perm[0] and of one rank; they become per-genome weight vectors.
 * list rows      -- genes whose shorter list (present or absent genomes) has fewer than
                     ``long_threshold`` entries: uint16 genome indices in 16-byte chunks,
-                    one lane per row, 32 rows of equal chunk count per warp task, chunks of a
-                    task interleaved so that a warp reads 512 contiguous bytes per step, and
+                    one lane per row, sub-blocks of 32 rows of equal chunk count, chunks of a
+                    sub-block interleaved so that a warp reads 512 contiguous bytes per step
+                    (a warp task streams a run of consecutive sub-blocks), and
                     the entries of every row ordered so that the lanes of a shared-memory
                     bank group hit distinct banks of the rank table.
 * bitmap rows    -- the remaining (long) genes as a genome-major bit-sliced bitmap (32 genes per
@@ -34,6 +35,8 @@ MAX_GENOMES = 65503          # genome indices, ranks and the 32 sentinel indices
 CHUNK = 8                    # indices per 16-byte chunk
 SENTINELS = 32               # rank-table rows N..N+31 hold 0xffff
 SUPERBLOCK = 1024            # bitmap rows per (superblock, genome) line of 128 bytes
+RUN_LANE_CHUNKS = 32         # most chunk iterations a warp streams per task (sub-blocks of 32 rows x chunks per row)
+RUN_TARGET_TASKS = 1024      # ... but small tables keep enough tasks to spread over the warps of a CTA row
 SMEM_TABLE_BUDGET = 220 * 1024
 
 
@@ -73,7 +76,8 @@ class HostPlan:
     n_full: int
     # list rows
     chunks: np.ndarray        # uint16 [n_chunks * 8]  task-interleaved, bank-ordered
-    tasks: np.ndarray         # int32  [n_tasks, 4]  {first_chunk, chunks_per_row | rows<<16 | absent<<24, first_row, 0}
+    tasks: np.ndarray         # int32  [n_tasks, 4]  {first_chunk, chunks_per_row | absent<<24, first_row, rows}: a run of
+                              #        ceil(rows / 32) consecutive sub-blocks of 32 rows x chunks_per_row chunks
     sorted_idx: np.ndarray    # uint16 [sum(row_len)]  the same lists, plainly sorted (mex probe)
     sorted_ptr: np.ndarray    # int32  [n_rows + 1]
     row_gene: np.ndarray      # int64  [n_rows] gene id of every list row (diagnostics / tests)
@@ -338,22 +342,36 @@ def build_host_plan(data, long_threshold=None, perms_per_cta=None) -> HostPlan:
         change = np.flatnonzero(np.diff(key)) + 1
         run_starts = np.concatenate(([0], change))
         run_ends = np.concatenate((change, [n_rows]))
-        t_first_row, t_rows, t_nch, t_abs = [], [], [], []
+        # sub-blocks of 32 rows (one lane per row) ...
+        b_first_row, b_rows, b_nch, b_abs, b_run = [], [], [], [], []
+        run_id = 0
+        total_iters = int(((run_ends - run_starts + 31) // 32 * n_chunk[run_starts]).sum())
+        run_budget = int(min(RUN_LANE_CHUNKS, max(2, total_iters // RUN_TARGET_TASKS)))
         for r0, r1 in zip(run_starts, run_ends):
             first_row = np.arange(r0, r1, 32, dtype=np.int64)
-            t_first_row.append(first_row)
-            t_rows.append(np.minimum(32, r1 - first_row))
-            t_nch.append(np.full(first_row.shape[0], n_chunk[r0], dtype=np.int64))
-            t_abs.append(np.full(first_row.shape[0], int(use_abs[r0]), dtype=np.int64))
-        t_first_row, t_rows, t_nch, t_abs = (np.concatenate(a) for a in (t_first_row, t_rows, t_nch, t_abs))
-        task_first = np.concatenate(([0], np.cumsum(t_nch * 32)))[:-1]
-        if (task_first[-1] + t_nch[-1] * 32) * CHUNK >= 2 ** 31:
+            nch = int(n_chunk[r0])
+            b_first_row.append(first_row)
+            b_rows.append(np.minimum(32, r1 - first_row))
+            b_nch.append(np.full(first_row.shape[0], nch, dtype=np.int64))
+            b_abs.append(np.full(first_row.shape[0], int(use_abs[r0]), dtype=np.int64))
+            # ... streamed by a warp in runs of about RUN_LANE_CHUNKS chunk iterations
+            per_run = max(1, run_budget // nch)
+            b_run.append(run_id + np.arange(first_row.shape[0]) // per_run)
+            run_id = int(b_run[-1][-1]) + 1
+        b_first_row, b_rows, b_nch, b_abs, b_run = (np.concatenate(a) for a in (b_first_row, b_rows, b_nch, b_abs, b_run))
+        block_first = np.concatenate(([0], np.cumsum(b_nch * 32)))[:-1]
+        if (block_first[-1] + b_nch[-1] * 32) * CHUNK >= 2 ** 31:
             raise ValueError("list rows too large for int32 chunk offsets")
-        if t_nch.max() >= 1 << 16:
+        if b_nch.max() >= 1 << 16:
             raise ValueError("list row too long for the task descriptor")
-        chunks = _bank_ordered_chunks(flat, ptr, task_first, t_nch, t_first_row, t_rows, n, modulus)
-        tasks = np.stack([task_first, t_nch | (t_rows << 16) | (t_abs << 24), t_first_row,
-                          np.zeros_like(task_first)], axis=1).astype(np.int32)
+        chunks = _bank_ordered_chunks(flat, ptr, block_first, b_nch, b_first_row, b_rows, n, modulus)
+        head = np.flatnonzero(np.concatenate(([True], np.diff(b_run) != 0)))       # first sub-block of every run
+        rows_in_run = np.add.reduceat(b_rows, head)
+        tasks = np.stack([block_first[head], b_nch[head] | (b_abs[head] << 24), b_first_row[head], rows_in_run],
+                         axis=1).astype(np.int32)
+        # costly runs first: dynamic fetching then ends on cheap ones
+        cost = b_nch[head] * ((rows_in_run + 31) // 32)
+        tasks = tasks[np.argsort(-cost, kind="stable")]
     else:
         chunks = np.zeros(0, dtype=np.uint16)
         tasks = np.zeros((0, 4), dtype=np.int32)

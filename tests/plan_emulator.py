@@ -23,13 +23,15 @@ def _mex_probe(perm, lst, n):
 def list_rows(hp):
     """Yields (row, absent_flag, entries-as-stored) by walking the task table like the kernel."""
     chunks = hp.chunks.reshape(-1, 8)
-    for first, meta, first_row, _ in hp.tasks:
+    for first, meta, first_row, n_rows in hp.tasks:
         meta = int(meta)
-        nch, n_rows, flag = meta & 0xFFFF, (meta >> 16) & 0xFF, (meta >> 24) & 1
-        assert 1 <= n_rows <= 32 and nch >= 1 and first % 32 == 0
-        for lane in range(n_rows):
-            stored = np.concatenate([chunks[first + it * 32 + lane] for it in range(nch)])
-            yield int(first_row) + lane, flag, stored.astype(np.int64)
+        nch, flag = meta & 0xFFFF, (meta >> 24) & 1
+        assert n_rows >= 1 and nch >= 1 and first % 32 == 0
+        for sub in range((int(n_rows) + 31) // 32):
+            base = int(first) + sub * nch * 32
+            for lane in range(min(32, int(n_rows) - 32 * sub)):
+                stored = np.concatenate([chunks[base + it * 32 + lane] for it in range(nch)])
+                yield int(first_row) + 32 * sub + lane, flag, stored.astype(np.int64)
 
 
 def check_layout(hp):
@@ -50,17 +52,19 @@ def check_layout(hp):
     assert covered.all()
     chunks = hp.chunks.reshape(-1, 8).astype(np.int64)
     wavefronts, steps = 0, 0
-    for first, meta, _, _ in hp.tasks:
+    for first, meta, _, n_rows in hp.tasks:
         nch = int(meta) & 0xFFFF
-        block = chunks[first:first + nch * 32].reshape(nch, 32, 8)      # [it][lane][j]
-        res = block % modulus
-        for g0 in range(0, 32, modulus):
-            grp = res[:, g0:g0 + modulus, :]                            # [it][lane in group][j]
-            counts = np.zeros((nch, 8, modulus), dtype=np.int64)
-            for lane in range(grp.shape[1]):
-                np.add.at(counts, (np.arange(nch)[:, None], np.arange(8)[None, :], grp[:, lane, :]), 1)
-            wavefronts += counts.max(axis=2).sum()
-            steps += nch * 8
+        for sub in range((int(n_rows) + 31) // 32):
+            base = int(first) + sub * nch * 32
+            block = chunks[base:base + nch * 32].reshape(nch, 32, 8)      # [it][lane][j]
+            res = block % modulus
+            for g0 in range(0, 32, modulus):
+                grp = res[:, g0:g0 + modulus, :]                            # [it][lane in group][j]
+                counts = np.zeros((nch, 8, modulus), dtype=np.int64)
+                for lane in range(grp.shape[1]):
+                    np.add.at(counts, (np.arange(nch)[:, None], np.arange(8)[None, :], grp[:, lane, :]), 1)
+                wavefronts += counts.max(axis=2).sum()
+                steps += nch * 8
     return wavefronts / max(1, steps)
 
 
