@@ -141,7 +141,7 @@ def run_reference(args, rank, world):
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # --------------------------------------------------------------------------------------
@@ -259,18 +259,36 @@ def run_b200(args, rank, world, local_rank):
     host_rng_s = time.time() - t
     d_perms = torch.empty((perms_n, n), dtype=torch.int16, device=device)
     d_perms.copy_(h_perms_owner)
-    d_out = torch.empty((perms_n, 2 * n), dtype=torch.int32, device=device)
-    gather_list = None
+    # N > 1: the curves of step i travel to rank 0 (NCCL gather over NVLink, asynchronous) while
+    # step i + 1 is computed into the other buffer; the timed region ends when every gather has landed.
+    n_buf = 2 if world > 1 else 1
+    d_outs = [torch.empty((perms_n, 2 * n), dtype=torch.int32, device=device) for _ in range(n_buf)]
+    d_out = d_outs[0]
+    gather_lists = [None] * n_buf
     if world > 1 and rank == 0:
-        gather_list = [torch.empty_like(d_out) for _ in range(world)]
+        gather_lists = [[torch.empty_like(d_out) for _ in range(world)] for _ in range(n_buf)]
+    pending = [None] * n_buf
+    step_no = [0]
 
     def step():
-        eng.curves_device(d_perms, out=d_out)
+        b = step_no[0] % n_buf
+        step_no[0] += 1
+        if pending[b] is not None:
+            pending[b].wait()                 # the buffer's previous gather has read it
+            pending[b] = None
+        eng.curves_device(d_perms, out=d_outs[b])
         if world > 1:
-            dist.gather(d_out, gather_list=gather_list, dst=0)
+            pending[b] = dist.gather(d_outs[b], gather_list=gather_lists[b], dst=0, async_op=True)
+
+    def drain():
+        for b in range(n_buf):
+            if pending[b] is not None:
+                pending[b].wait()
+                pending[b] = None
 
     for _ in range(max(args.warmup, 3)):
         step()
+    drain()
     torch.cuda.synchronize()
 
     sampler = ClockSampler(local_rank) if rank == 0 else None
@@ -283,6 +301,7 @@ def run_b200(args, rank, world, local_rank):
     e0.record()
     for _ in range(args.steps):
         step()
+    drain()
     e1.record()
     torch.cuda.synchronize()
     w1 = time.perf_counter()
@@ -391,7 +410,8 @@ def run_b200(args, rank, world, local_rank):
     config = workload_config(args.workload, coo, perms_n, world)
     config["l2_policy"] = "inputs larger than L2: %.0f MB of permutations + %.0f MB of curves + %.0f MB of folded rows per step" % (
         d_perms.numel() * 2 / 1e6, d_out.numel() * 4 / 1e6, hp.streamed_bytes_per_pass / 1e6)
-    config["gather"] = "NCCL gather of int32 curves to rank 0 inside the timed region" if world > 1 else "none (1 GPU)"
+    config["gather"] = ("NCCL gather of int32 curves to rank 0 inside the timed region, asynchronous, "
+                        "overlapped with the next step (two output buffers)") if world > 1 else "none (1 GPU)"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
@@ -399,13 +419,27 @@ def run_b200(args, rank, world, local_rank):
         "cells_per_s": value * n_genes * n, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks, "host_rng_s_for_perms": host_rng_s,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
     if world > 1:
         dist.destroy_process_group()
 
 
+_JSON_OUT = None
+
+
+def emit(line):
+    """The one JSON line goes to the real stdout; everything else any library prints (NCCL's
+    version banner, ...) was redirected to stderr in main()."""
+    _JSON_OUT.write(json.dumps(line) + "\n")
+    _JSON_OUT.flush()
+
+
 def main():
+    global _JSON_OUT
     args = parse_args()
+    sys.stdout.flush()
+    _JSON_OUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)                                  # fd 1 -> stderr for C libraries and stray prints
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
