@@ -41,6 +41,7 @@ __device__ __forceinline__ double warp_sum(double v)
 
 __global__ void __launch_bounds__(BG_THREADS)
 grid_kernel(const uint32_t *__restrict__ xbits, const BernoulliShape shape,
+            const int32_t *__restrict__ row_count,
             const double *__restrict__ p, const double *__restrict__ q,
             double *__restrict__ gp_part,   // [col_tiles][G]
             double *__restrict__ gq_part,   // [row_tiles][N]
@@ -90,6 +91,8 @@ grid_kernel(const uint32_t *__restrict__ xbits, const BernoulliShape shape,
         }
         gp = warp_sum(gp);
         if (lane == 0) gp_part[static_cast<long long>(col_tile) * shape.n_genes + i] = gp;
+        // closed-form term of the present cells of this gene, m_i log p_i, counted once (column tile 0)
+        if (lane == 0 && col_tile == 0) ll += static_cast<double>(row_count[i]) * log(pi);
     }
 
     // combine the warps' column sums in warp order
@@ -138,8 +141,6 @@ finish_kernel(const BernoulliShape shape, const int32_t *__restrict__ row_count,
     if (blockIdx.x == 0) {
         __shared__ double s_part[256];
         double s = 0.0;
-        for (long long i = threadIdx.x; i < shape.n_genes; i += 256)
-            s += static_cast<double>(row_count[i]) * log(p[i]);
         for (long long j = threadIdx.x; j < shape.n_genomes; j += 256)
             s += static_cast<double>(col_count[j]) * log(q[j]);
         const long long n_part = static_cast<long long>(shape.row_tiles) * shape.col_tiles;
@@ -204,7 +205,7 @@ int pgx_bernoulli_ll_grad(const uint32_t *d_xbits, int64_t words_per_row, int64_
     double *gq_part = gp_part + static_cast<size_t>(s.col_tiles) * n_genes;
     double *ll_part = gq_part + static_cast<size_t>(s.row_tiles) * n_genomes;
     dim3 grid(s.row_tiles, s.col_tiles);
-    pgx::grid_kernel<<<grid, pgx::BG_THREADS, 0, st>>>(d_xbits, s, d_p, d_q, gp_part, gq_part, ll_part);
+    pgx::grid_kernel<<<grid, pgx::BG_THREADS, 0, st>>>(d_xbits, s, d_row_count, d_p, d_q, gp_part, gq_part, ll_part);
     PGX_LAUNCH_CHECK("bernoulli grid_kernel");
     const long long total = n_genes + n_genomes;
     pgx::finish_kernel<<<static_cast<unsigned>((total + 255) / 256), 256, 0, st>>>(

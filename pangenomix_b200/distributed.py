@@ -117,5 +117,4 @@ def estimate_pan_core_size_sharded(df_genes, num_iter, log_batch=-1, group=None,
     iter_index = ['Iter' + str(x) for x in range(1, num_iter + 1)]
     pan_cols = ['Pan' + str(x) for x in range(1, num_strains + 1)]
     core_cols = ['Core' + str(x) for x in range(1, num_strains + 1)]
-    return pd.DataFrame(index=iter_index, columns=pan_cols + core_cols,
-                        data=curves.astype(np.float64))
+    return pd.DataFrame(curves.astype(np.float64), index=iter_index, columns=pan_cols + core_cols, copy=False)

@@ -168,28 +168,59 @@ class PanCoreEngine:
         return out
 
     # ---- the reference's call: draw from np.random, return float64 (num_iter, 2N) -----
+    def _estimate_buffers(self, block):
+        """Staging of ``estimate``: two slots of pinned host + device buffers, kept across calls."""
+        torch = _torch()
+        cached = getattr(self, "_est", None)
+        if cached is not None and cached["block"] >= block:
+            return cached
+        n = self.n_genomes
+        with torch.cuda.device(self.device):
+            self._est = {
+                "block": block,
+                "streams": [torch.cuda.Stream(self.device) for _ in range(2)],
+                "h_perm": [pinned_empty((block, n), np.uint16) for _ in range(2)],
+                "h_out": [pinned_empty((block, 2 * n), np.float64) for _ in range(2)],
+                "d_perm": [torch.empty((block, n), dtype=torch.int16, device=self.device) for _ in range(2)],
+                "d_hist": [torch.empty((block, 2 * n), dtype=torch.int32, device=self.device) for _ in range(2)],
+                "d_out": [torch.empty((block, 2 * n), dtype=torch.float64, device=self.device) for _ in range(2)],
+            }
+        return self._est
+
     def estimate(self, num_iter, log_batch=-1, block=None):
         """pangenome_analysis.py:76-90: curves for ``num_iter`` shuffles of the global RNG.
 
-        Host shuffles of block k+1 overlap the H2D copy, kernels and D2H copy of block k.
+        Blocks of permutations flow through two slots: while the GPU works on block k (H2D,
+        kernels, D2H into pinned staging), the host draws the shuffles of block k+1 and a helper
+        thread moves the finished curves of block k-1 into the (ordinary, pageable) result.
         """
+        import concurrent.futures
         torch = _torch()
         num_iter = int(num_iter)
         n = self.n_genomes
-        out, out_owner = pinned_empty((num_iter, 2 * n), np.float64)
+        out = np.empty((num_iter, 2 * n), dtype=np.float64)
         if num_iter == 0:
             return out
-        if block is None:
-            block = max(32, min(4096, (32 << 20) // (16 * n)))
-        block = max(1, min(int(block), num_iter))
-        out_t = out_owner
-        with torch.cuda.device(self.device):
-            streams = [torch.cuda.Stream(self.device) for _ in range(2)]
-            stage = [pinned_empty((block, n), np.uint16) for _ in range(2)]
-            d_perm = [torch.empty((block, n), dtype=torch.int16, device=self.device) for _ in range(2)]
-            d_hist = [torch.empty((block, 2 * n), dtype=torch.int32, device=self.device) for _ in range(2)]
-            d_out = [torch.empty((block, 2 * n), dtype=torch.float64, device=self.device) for _ in range(2)]
-            done = [None, None]
+        default_block = max(32, min(4096, (32 << 20) // (16 * n)))
+        block = default_block if block is None else max(1, int(block))
+        buf = self._estimate_buffers(max(block, default_block))       # sized once, reused by later calls
+        block = max(1, min(block, num_iter))
+        streams = buf["streams"]
+        done = [None, None]            # (event, first row, count) of the block in flight in each slot
+        copies = [None, None]          # future of the slot's last staging -> result copy
+
+        def retire(slot):
+            if done[slot] is None:
+                return
+            ev, p0, cnt = done[slot]
+            done[slot] = None
+
+            def move():
+                ev.synchronize()
+                np.copyto(out[p0:p0 + cnt], buf["h_out"][slot][0][:cnt])
+            copies[slot] = pool.submit(move)
+
+        with torch.cuda.device(self.device), concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
             slot = 0
             for p0 in range(0, num_iter, block):
                 cnt = min(block, num_iter - p0)
@@ -197,23 +228,26 @@ class PanCoreEngine:
                     first = ((p0 + log_batch) // log_batch) * log_batch
                     for it in range(first, p0 + cnt + 1, log_batch):
                         print('\tIteration', it, 'of', num_iter)       # :82-83
-                if done[slot] is not None:
-                    done[slot].synchronize()         # staging buffer free again
-                host_perm, host_owner = stage[slot]
+                if copies[slot] is not None:
+                    copies[slot].result()            # the slot's staging buffers are free again
+                    copies[slot] = None
+                host_perm, host_owner = buf["h_perm"][slot]
                 draw_legacy_permutations(n, cnt, out=host_perm[:cnt])
                 with torch.cuda.stream(streams[slot]):
-                    d_perm[slot][:cnt].copy_(host_owner[:cnt], non_blocking=True)
+                    buf["d_perm"][slot][:cnt].copy_(host_owner[:cnt], non_blocking=True)
                     _native.check(self.lib.pgx_pan_core_curves_f64(
-                        ctypes.byref(self.c_plan), d_perm[slot].data_ptr(), cnt,
-                        d_hist[slot].data_ptr(), d_out[slot].data_ptr(),
+                        ctypes.byref(self.c_plan), buf["d_perm"][slot].data_ptr(), cnt,
+                        buf["d_hist"][slot].data_ptr(), buf["d_out"][slot].data_ptr(),
                         streams[slot].cuda_stream))
-                    out_t[p0:p0 + cnt].copy_(d_out[slot][:cnt], non_blocking=True)
+                    buf["h_out"][slot][1][:cnt].copy_(buf["d_out"][slot][:cnt], non_blocking=True)
                     ev = torch.cuda.Event()
                     ev.record(streams[slot])
-                    done[slot] = ev
+                done[slot] = (ev, p0, cnt)
+                retire(slot)                        # the helper waits for the GPU, then copies
                 slot ^= 1
-            for s in streams:
-                s.synchronize()
+            for s in range(2):
+                if copies[s] is not None:
+                    copies[s].result()
         return out
 
 

@@ -93,7 +93,8 @@ def estimate_pan_core_size(df_genes, num_iter, log_batch=-1, device=None):
     iter_index = ['Iter' + str(x) for x in range(1, num_iter + 1)]
     pan_cols = ['Pan' + str(x) for x in range(1, num_strains + 1)]
     core_cols = ['Core' + str(x) for x in range(1, num_strains + 1)]
-    return pd.DataFrame(index=iter_index, columns=pan_cols + core_cols, data=curves)
+    # the curves are a fresh array nobody else holds: wrap it instead of copying it (pandas 3 copies by default)
+    return pd.DataFrame(curves, index=iter_index, columns=pan_cols + core_cols, copy=False)
 
 
 def compute_bernoulli_grid_core_genome(df_genes_dense,

@@ -36,6 +36,7 @@ CHUNK = 8                    # indices per 16-byte chunk
 SENTINELS = 32               # rank-table rows N..N+31 hold 0xffff
 SUPERBLOCK = 1024            # bitmap rows per (superblock, genome) line of 128 bytes
 RUN_LANE_CHUNKS = 32         # most chunk iterations a warp streams per task (sub-blocks of 32 rows x chunks per row)
+COLOUR_MAX_CHUNKS = 32       # rows of more chunks than this use the cheap positional bank ordering
 RUN_TARGET_TASKS = 1024      # ... but small tables keep enough tasks to spread over the warps of a CTA row
 SMEM_TABLE_BUDGET = 220 * 1024
 
@@ -198,65 +199,142 @@ def _folded_lists(indptr, indices, m, genes, use_abs, length, n):
     return flat, ptr
 
 
-def _bank_ordered_chunks(flat, ptr, task_first, task_nch, task_first_row, task_rows, n, modulus):
+def _colour_groups(cnt, n_steps):
+    """Greedy edge colouring, vectorised over wavefront groups.
+
+    ``cnt[g, l, r]`` = entries of residue r in the row of lane l of group g (all rows of a group
+    gather in lock step from one shared-memory wavefront).  Chooses for every (group, lane, step) a
+    residue, or -1 for a pad, such that every entry gets a step and, wherever possible, the lanes
+    of a group use distinct residues at a step (a conflict-free wavefront).  This is edge colouring
+    of the bipartite multigraph lanes x residues with ``n_steps`` colours; the greedy rule
+    (critical residues first, rows without slack may not pass) gets within a few percent of the
+    optimum max(lane degree, residue degree) / n_steps.
+    Returns (res_at [G, R, S] int8, pad_res [G, R, S] int8).
+    """
+    n_groups, r_mod, _ = cnt.shape
+    cnt = cnt.astype(np.int32, copy=True)
+    res_at = np.full((n_groups, r_mod, n_steps), -1, dtype=np.int8)
+    pad_res = np.zeros((n_groups, r_mod, n_steps), dtype=np.int8)
+    colload = cnt.sum(axis=1)                      # [G, residue]
+    rem = cnt.sum(axis=2)                          # [G, lane]
+    ar = np.arange(n_groups)
+    for s in range(n_steps):
+        taken = np.zeros((n_groups, r_mod), dtype=bool)
+        steps_left = n_steps - s
+        # rows with the least slack choose first
+        order = np.argsort(steps_left - rem, axis=1, kind="stable")           # [G, lane rank] -> lane
+        for t in range(r_mod):
+            lane = order[:, t]
+            c = cnt[ar, lane]                      # [G, residue]
+            avail = (c > 0) & ~taken
+            score = np.where(avail, colload * 1024 + c, -1)
+            choice = score.argmax(axis=1)
+            has = avail[ar, choice]
+            forced = ~has & (rem[ar, lane] >= steps_left) & (rem[ar, lane] > 0)
+            if forced.any():
+                choice = np.where(forced, c.argmax(axis=1), choice)
+            idx = np.flatnonzero(has | forced)
+            if idx.size:
+                li, ch = lane[idx], choice[idx]
+                res_at[idx, li, s] = ch
+                cnt[idx, li, ch] -= 1
+                colload[idx, ch] -= 1
+                rem[idx, li] -= 1
+                taken[idx, ch] = True
+        # pads: the k-th idle lane of a group takes the group's k-th unused residue
+        idle = res_at[:, :, s] < 0
+        if idle.any():
+            free_order = np.argsort(taken, axis=1, kind="stable")             # unused residues first
+            rank = np.cumsum(idle, axis=1) - 1
+            pad_res[:, :, s] = np.where(idle, np.take_along_axis(free_order, np.clip(rank, 0, r_mod - 1), axis=1), 0)
+    assert not cnt.any()
+    return res_at, pad_res
+
+
+def _positional_groups(cnt, n_steps):
+    """Cheap stand-in for ``_colour_groups`` for very long rows (whose residues are well balanced
+    anyway): lane l wants residue (s + l) % R at step s and takes it while it has such entries;
+    surplus entries fill the lane's unused steps in order.  Same return convention."""
+    n_groups, r_mod, _ = cnt.shape
+    steps = np.arange(n_steps)
+    lanes = np.arange(r_mod)
+    want = (steps[None, :] + lanes[:, None]) % r_mod                         # [lane, step]
+    occ = steps[None, :] // r_mod                                            # how many earlier steps wanted the same residue
+    have = np.take_along_axis(cnt, np.broadcast_to(want[None], (n_groups, r_mod, n_steps)), axis=2)
+    placed = occ[None] < have                                                # [G, lane, step]
+    res_at = np.where(placed, want[None], -1).astype(np.int8)
+    # surplus entries of a lane, residue by residue, into its unused steps in order
+    used = placed.reshape(n_groups, r_mod, n_steps)
+    per_res_cap = np.zeros((n_groups, r_mod, r_mod), dtype=np.int64)         # steps that want residue r for lane l
+    for r in range(r_mod):
+        per_res_cap[:, :, r] = (want == r).sum(axis=1)[None, :]
+    surplus = np.maximum(cnt - per_res_cap, 0)                               # [G, lane, residue]
+    g_idx, l_idx = np.nonzero(surplus.sum(axis=2))
+    for g, l in zip(g_idx, l_idx):
+        free = np.flatnonzero(~used[g, l])
+        extra = np.repeat(np.arange(r_mod), surplus[g, l])
+        res_at[g, l, free[:extra.size]] = extra
+    pad_res = np.broadcast_to(want[None], (n_groups, r_mod, n_steps)).astype(np.int8)
+    return res_at, pad_res
+
+
+def _bank_ordered_chunks(flat, ptr, block_first, block_nch, block_first_row, block_rows, n, modulus):
     """Lays the list rows out for the lane-per-row kernel.
 
-    Lane l of a task reads chunk ``first + it * 32 + l`` at iteration ``it`` and gathers the
-    rank-table line of the chunk's j-th index at step s = 8 it + j.  The lanes of one
-    shared-memory wavefront (``modulus`` consecutive lanes) are conflict-free when their
-    indices differ modulo ``modulus``, so an entry of residue r = index % modulus is stored
-    at a step with (s + l) % modulus == r while the row has such steps left; surplus
-    entries take the row's unused steps, and steps still unused keep a sentinel index
-    (>= N) of the matching residue.
+    Lane l of a sub-block reads chunk ``first + it * 32 + l`` at iteration ``it`` and gathers the
+    rank-table line of the chunk's j-th index at step s = 8 it + j.  The lanes of one shared-memory
+    wavefront (``modulus`` consecutive lanes) are conflict-free when their indices differ modulo
+    ``modulus``; which entry of a row goes to which step is decided by ``_colour_groups``.  Unused
+    steps hold a sentinel index (>= N) of a residue nobody else uses at that step.
     """
-    n_tasks = task_nch.shape[0]
-    slots_per_task = task_nch * (32 * CHUNK)
-    n_slots = int(slots_per_task.sum())
-    slot = np.arange(n_slots, dtype=np.int64)
-    task_of_slot = np.repeat(np.arange(n_tasks), slots_per_task)
-    lane_of_slot = (slot >> 3) & 31                     # tasks start at multiples of 32 chunks
-    it_of_slot = ((slot >> 3) - task_first[task_of_slot]) >> 5
-    want = (it_of_slot * 8 + (slot & 7) + lane_of_slot) % modulus
-    chunks = (n + ((want - n) % modulus)).astype(np.uint16)
-    del want, it_of_slot
-    if flat.size == 0:
-        return chunks
-
+    n_blocks = block_nch.shape[0]
+    n_slots = int((block_nch * (32 * CHUNK)).sum())
+    chunks = np.empty(n_slots, dtype=np.uint16)
     lens = np.diff(ptr)
     n_rows = lens.shape[0]
-    row_task = np.repeat(np.arange(n_tasks), task_rows)
-    row_lane = np.arange(n_rows) - task_first_row[row_task]
+    row_block = np.repeat(np.arange(n_blocks), block_rows)
+    row_lane = np.arange(n_rows) - block_first_row[row_block]
+    groups_per_block = 32 // modulus
     row_of_entry = np.repeat(np.arange(n_rows), lens)
-    res = flat % modulus
-    order = np.lexsort((flat, res, row_of_entry))           # by (row, residue, index)
-    row_s, res_s, idx_s = row_of_entry[order], res[order], flat[order]
-    key = row_s * modulus + res_s
-    starts = np.flatnonzero(np.concatenate(([True], key[1:] != key[:-1])))
-    run_len = np.diff(np.concatenate((starts, [key.shape[0]])))
-    occ = np.arange(key.shape[0]) - np.repeat(starts, run_len)
-    lane = row_lane[row_s]
-    step = ((res_s - lane) % modulus) + modulus * occ
-    placed = step < task_nch[row_task[row_s]] * 8
-    addr = ((task_first[row_task[row_s]] + (step >> 3) * 32 + lane) << 3) + (step & 7)
-    filled = np.zeros(n_slots, dtype=bool)
-    chunks[addr[placed]] = idx_s[placed].astype(np.uint16)
-    filled[addr[placed]] = True
-
-    over = np.flatnonzero(~placed)
-    if over.size:
-        # the k-th surplus entry of a row takes the row's k-th free slot
-        over_row = row_s[over]                               # sorted by row already
-        real = lane_of_slot < task_rows[task_of_slot]
-        free = np.flatnonzero(real & ~filled)
-        free_row = task_first_row[task_of_slot[free]] + lane_of_slot[free]
-        by_row = np.argsort(free_row, kind="stable")
-        free, free_row = free[by_row], free_row[by_row]
-        free_start = np.searchsorted(free_row, np.arange(n_rows), side="left")
-        over_start = np.searchsorted(over_row, np.arange(n_rows), side="left")
-        k = np.arange(over.size) - over_start[over_row]
-        dest = free[free_start[over_row] + k]
-        assert np.array_equal(free_row[free_start[over_row] + k], over_row)
-        chunks[dest] = idx_s[over].astype(np.uint16)
+    res_of_entry = (flat % modulus).astype(np.int64)
+    # entries sorted by (row, residue, index): the k-th entry of a (row, residue) pair takes the
+    # k-th step the colouring gave that pair
+    e_order = np.lexsort((flat, res_of_entry, row_of_entry))
+    e_sorted_idx = flat[e_order]
+    for nch in np.unique(block_nch):
+        blocks = np.flatnonzero(block_nch == nch)
+        n_steps = int(nch) * CHUNK
+        local_block = np.full(n_blocks, -1, dtype=np.int64)
+        local_block[blocks] = np.arange(blocks.size)
+        in_class = local_block[row_block[row_of_entry]] >= 0
+        ent = np.flatnonzero(in_class)
+        g = local_block[row_block[row_of_entry[ent]]] * groups_per_block + row_lane[row_of_entry[ent]] // modulus
+        l = row_lane[row_of_entry[ent]] % modulus
+        n_groups = blocks.size * groups_per_block
+        cnt = np.bincount((g * modulus + l) * modulus + res_of_entry[ent],
+                          minlength=n_groups * modulus * modulus).reshape(n_groups, modulus, modulus)
+        if nch <= COLOUR_MAX_CHUNKS:
+            res_at, pad_res = _colour_groups(cnt, n_steps)
+        else:
+            res_at, pad_res = _positional_groups(cnt, n_steps)
+        # slot address of (group, lane, step)
+        gg, ll, ss = np.meshgrid(np.arange(n_groups), np.arange(modulus), np.arange(n_steps), indexing="ij")
+        blk = blocks[gg // groups_per_block]
+        lane32 = (gg % groups_per_block) * modulus + ll
+        addr = ((block_first[blk] + (ss >> 3) * 32 + lane32) << 3) + (ss & 7)
+        is_pad = res_at < 0
+        chunks[addr[is_pad]] = (n + ((pad_res[is_pad].astype(np.int64) - n) % modulus)).astype(np.uint16)
+        # real slots sorted by (row, residue, step) line up with the class's entries sorted by (row, residue, index)
+        real = ~is_pad
+        slot_row = (block_first_row[blk] + lane32)[real]
+        slot_res = res_at[real].astype(np.int64)
+        slot_step = ss[real]
+        slot_addr = addr[real]
+        s_order = np.lexsort((slot_step, slot_res, slot_row))
+        cls_sorted = e_order[in_class[e_order]]                  # entries of this class in (row, residue, index) order
+        assert cls_sorted.shape[0] == s_order.shape[0]
+        assert np.array_equal(row_of_entry[cls_sorted], slot_row[s_order])
+        chunks[slot_addr[s_order]] = flat[cls_sorted].astype(np.uint16)
     return chunks
 
 

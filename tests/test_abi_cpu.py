@@ -59,6 +59,33 @@ def test_legacy_shuffles_are_numpys(n):
     assert np.array_equal(a, np.random.random_sample(3))
 
 
+@pytest.mark.parametrize("n,count", [(7, 5000), (64, 3000), (400, 2500), (10000, 120), (65503, 24)])
+@pytest.mark.parametrize("mode", ["default", "scalar", "one_thread", "seven_threads"])
+def test_legacy_shuffles_vector_and_threaded_paths(monkeypatch, n, count, mode):
+    """Long streams exercise the AVX2 acceptance spans, every mask boundary, MT19937 block
+    boundaries inside a vector and the producer / worker-thread pipeline; all must equal numpy."""
+    if mode == "scalar":
+        monkeypatch.setenv("PGX_RNG_SCALAR", "1")
+    elif mode == "one_thread":
+        monkeypatch.setenv("PGX_RNG_THREADS", "0")
+    elif mode == "seven_threads":
+        monkeypatch.setenv("PGX_RNG_THREADS", "7")
+    np.random.seed(2024)
+    np.random.random_sample(77)
+    start = np.random.get_state()
+    got = engine.draw_legacy_permutations(n, count)
+    after = np.random.get_state()
+    np.random.set_state(start)
+    want = np.empty((count, n), dtype=np.uint16)
+    for i in range(count):
+        a = np.arange(n)
+        np.random.shuffle(a)
+        want[i] = a
+    ref_after = np.random.get_state()
+    assert np.array_equal(got, want)
+    assert np.array_equal(after[1], ref_after[1]) and after[2] == ref_after[2]
+
+
 def test_legacy_shuffles_mid_block_state_and_numpy_mode(monkeypatch):
     np.random.seed(99)
     np.random.random_sample(123)           # leave the generator mid-block
