@@ -291,6 +291,7 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
 #pragma unroll
             for (int j = 0; j < SLICE_DEPTH; ++j) {
                 const uint32_t flipped = d[j] & pending;
+                if (!__any_sync(FULL_MASK, flipped)) continue;      // mid / late walk: most single steps flip nothing
                 pending &= ~flipped;
                 // low half: genes first seen at k (pan side); high half: genes first missed at k (core side)
                 const uint32_t packed = __popc(flipped & ~b0) | (__popc(flipped & b0) << 16);
