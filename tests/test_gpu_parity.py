@@ -192,6 +192,63 @@ def test_c4_shape_sample(engine_mod):
     assert np.array_equal(pan[:, 0], core[:, 0])
 
 
+def test_c4_full_size_properties_and_spot_parity(engine_mod):
+    """Config C4 at BASELINE.json's full size (200,000 genes x 10,000 genomes): size-independent
+    invariants on 1,000 curves, oracle parity on two of them, and the two-stream and
+    back-to-back kernel schedules must agree bit for bit."""
+    import os
+    from oracle import build as oracle_build, cport
+    from pangenomix_b200 import _native, synth
+    coo = synth.config_matrix("c4")
+    eng = engine_mod.PanCoreEngine(coo)
+    hp = eng.host_plan
+    assert hp.n_long > 0 and hp.n_rows > 0 and hp.perms_per_cta == 8
+    n, g = 10000, 200000
+    np.random.seed(12345)
+    perms = engine_mod.draw_legacy_permutations(n, 1000)
+    curves = eng.curves_host(perms)
+    pan, core = curves[:, :n], curves[:, n:]
+    counts = np.diff(coo.tocsr().indptr)
+    assert np.all(np.diff(pan, axis=1) >= 0) and np.all(np.diff(core, axis=1) <= 0)
+    assert np.array_equal(pan[:, 0], core[:, 0])
+    assert np.all(pan[:, -1] == np.count_nonzero(counts)) and np.all(core[:, -1] == np.count_nonzero(counts == n))
+    col_sums = np.asarray(coo.sum(axis=0)).ravel()
+    assert np.array_equal(pan[:, 0], col_sums[perms[:, 0]])
+    # sum over k of pan[k] = sum over genes of (N - first presence): a checksum of checksums against numpy
+    oracle_build.build()
+    sample = [0, 999]
+    ref_pan, ref_core = cport.curves_direct(coo, perms[sample].astype(np.int32), n_threads=os.cpu_count() or 1)
+    assert np.array_equal(curves[sample], np.hstack([ref_pan, ref_core]).astype(np.int32))
+    # per-kernel timing mode runs the row kernels back to back instead of side by side
+    _native.profile_enable(True)
+    try:
+        again = eng.curves_host(perms[:200])
+    finally:
+        _native.profile_enable(False)
+        _native.profile_read()
+    assert np.array_equal(again, curves[:200])
+
+
+def test_estimate_blocks_progress_and_rng_state(engine_mod, capsys):
+    """engine.estimate: several staging blocks, a ragged last block, progress lines, RNG consumption."""
+    from pangenomix_b200 import synth
+    coo = synth.bernoulli_matrix(3000, 300, 450, seed=1)
+    eng = engine_mod.PanCoreEngine(coo)
+    np.random.seed(5)
+    got = eng.estimate(70, log_batch=25, block=16)
+    tail = np.random.random_sample(3)
+    out = capsys.readouterr().out
+    assert [l for l in out.splitlines() if l.startswith("\tIteration")] == [
+        "\tIteration 25 of 70", "\tIteration 50 of 70"]
+    perms = draw_perms(5, 300, 70)
+    assert np.array_equal(tail, np.random.random_sample(3))
+    assert got.dtype == np.float64 and np.array_equal(got, _oracle_curves(coo, perms).astype(np.float64))
+    # a second call reuses the staging buffers and may use a different block size
+    np.random.seed(5)
+    assert np.array_equal(eng.estimate(70), got)
+    assert eng.estimate(0).shape == (0, 600)
+
+
 # ---------------------------------------------------------------------------------------
 # Bernoulli grid
 # ---------------------------------------------------------------------------------------
