@@ -266,27 +266,27 @@ def run_b200(args, rank, world, local_rank):
     n_buf = 2 if world > 1 else 1
     d_outs = [torch.empty((perms_n, 2 * n), dtype=torch.int32, device=device) for _ in range(n_buf)]
     d_out = d_outs[0]
-    gather_lists = [None] * n_buf
-    if world > 1 and rank == 0:
-        gather_lists = [[torch.empty_like(d_out) for _ in range(world)] for _ in range(n_buf)]
-    pending = [None] * n_buf
+    gather = None
+    if world > 1:
+        from pangenomix_b200.distributed import CurveGather
+        gather = CurveGather(perms_n, 2 * n, device, dst=0, n_buffers=n_buf,
+                             prefer_peer=os.environ.get("PGX_GATHER", "peer") != "nccl")
+        log("[bench r%d] curve gather: %s%s" % (rank, gather.mode,
+                                                 "" if gather.mode == "peer-push" else " (%s)" % getattr(gather, "fallback_reason", "requested")))
     step_no = [0]
 
     def step():
         b = step_no[0] % n_buf
         step_no[0] += 1
-        if pending[b] is not None:
-            pending[b].wait()                 # the buffer's previous gather has read it
-            pending[b] = None
+        if gather is not None:
+            gather.before_overwrite(b)        # the buffer's previous transfer has read it
         eng.curves_device(d_perms, out=d_outs[b])
-        if world > 1:
-            pending[b] = dist.gather(d_outs[b], gather_list=gather_lists[b], dst=0, async_op=True)
+        if gather is not None:
+            gather.send(b, d_outs[b])
 
     def drain():
-        for b in range(n_buf):
-            if pending[b] is not None:
-                pending[b].wait()
-                pending[b] = None
+        if gather is not None:
+            gather.drain()
 
     for _ in range(max(args.warmup, 3)):
         step()
@@ -326,6 +326,18 @@ def run_b200(args, rank, world, local_rank):
     row_ms = list_ms + probe_ms
     _native.profile_enable(False)
     ms_per_step = ms_total / args.steps
+
+    # the gathered blocks really are on rank 0 (its own block bit for bit, the others by invariants)
+    if gather is not None:
+        barrier()
+        if rank == 0:
+            b_last = (step_no[0] - 1) % n_buf
+            got = gather.gathered(b_last)
+            assert torch.equal(got[0], d_outs[b_last])
+            far = got[world - 1][:16].cpu().numpy()
+            assert np.all(np.diff(far[:, :n], axis=1) >= 0) and np.array_equal(far[:, 0], far[:, n])
+            assert far[:, n - 1].min() > 0 and not np.array_equal(far, d_outs[b_last][:16].cpu().numpy())
+        barrier()
 
     # parity guard on the timed output (size-independent invariants, cheap)
     curves = d_out[:64].cpu().numpy()
@@ -443,8 +455,15 @@ def run_b200(args, rank, world, local_rank):
     config = workload_config(args.workload, coo, perms_n, world)
     config["l2_policy"] = "inputs larger than L2: %.0f MB of permutations + %.0f MB of curves + %.0f MB of folded rows per step" % (
         d_perms.numel() * 2 / 1e6, d_out.numel() * 4 / 1e6, hp.streamed_bytes_per_pass / 1e6)
-    config["gather"] = ("NCCL gather of int32 curves to rank 0 inside the timed region, asynchronous, "
-                        "overlapped with the next step (two output buffers)") if world > 1 else "none (1 GPU)"
+    if world > 1 and gather.mode == "peer-push":
+        config["gather"] = ("int32 curves of every rank pushed into rank 0's symmetric-memory buffer over NVLink "
+                            "(copy-engine peer copies on a side stream) inside the timed region, overlapped with "
+                            "the next step (two buffers)")
+    elif world > 1:
+        config["gather"] = ("NCCL gather of int32 curves to rank 0 inside the timed region, asynchronous, "
+                            "overlapped with the next step (two output buffers)")
+    else:
+        config["gather"] = "none (1 GPU)"
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,

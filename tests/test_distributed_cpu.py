@@ -74,3 +74,43 @@ def test_shard_bounds_cover_everything():
             assert all(blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
             sizes = [hi - lo for lo, hi in blocks]
             assert max(sizes) - min(sizes) <= 1
+
+
+def _gather_worker(rank, world, port, result_dir):
+    sys.path.insert(0, REPO)
+    import numpy as np
+    import torch
+    import torch.distributed as dist
+    from pangenomix_b200.distributed import CurveGather
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rows, width = 5, 12
+    gather = CurveGather(rows, width, "cpu", dst=0, n_buffers=2)
+    assert gather.mode == "nccl-gather"            # no peer memory on CPU: the collective path
+    last = {}
+    for step in range(5):                          # more steps than buffers: reuse after before_overwrite
+        b = step % 2
+        gather.before_overwrite(b)
+        block = torch.full((rows, width), 1000 * step + rank, dtype=torch.int32)
+        gather.send(b, block)
+        last[b] = step
+    gather.drain()
+    dist.barrier()
+    if rank == 0:
+        for b, step in last.items():
+            got = gather.gathered(b).numpy()
+            assert got.shape == (world, rows, width)
+            for r in range(world):
+                assert np.all(got[r] == 1000 * step + r)
+        np.save(os.path.join(result_dir, "ok.npy"), np.ones(1))
+    else:
+        assert gather.gathered(0) is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_curve_gather_collective_path(tmp_path, world):
+    mp.spawn(_gather_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    assert os.path.exists(str(tmp_path / "ok.npy"))
