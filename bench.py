@@ -401,6 +401,35 @@ def run_b200(args, rank, world, local_rank):
                        "H2D/D2H and the float64 DataFrame; the table was already resident" % iters}
         del df
 
+    # ---- next row of the scope table: Heaps-law fits of every curve of the step, on the device ----
+    heaps = None
+    if rank == 0 and not args.no_e2e:
+        import warnings
+        import pandas as pd
+        from pangenomix_b200 import pangenome_analysis as pa
+        engine.fit_heaps_device(d_out[:8])
+        torch.cuda.synchronize()
+        h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        h0.record()
+        fit, info = engine.fit_heaps_device(d_out)
+        h1.record()
+        torch.cuda.synchronize()
+        fit_ms = h0.elapsed_time(h1)
+        sample = d_out[:3].cpu().numpy().astype(np.float64)
+        cols = ["Pan%d" % (i + 1) for i in range(n)] + ["Core%d" % (i + 1) for i in range(n)]
+        t0 = time.perf_counter()
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            want = pa.fit_heaps_by_iteration(pd.DataFrame(sample, columns=cols))
+        scipy_s = (time.perf_counter() - t0) / 3
+        np.testing.assert_allclose(fit[:3].cpu().numpy(), want.values, rtol=5e-6)
+        heaps = {"call": "pgx_heaps_fit on the %d device-resident curves of one step (%d points each)" % (perms_n, n),
+                 "value": perms_n / (fit_ms / 1e3), "unit": "fits/s", "ms": fit_ms,
+                 "converged": int((info > 0).sum().item()),
+                 "scipy_curve_fit_fits_per_s": 1.0 / scipy_s,
+                 "note": "fit_heaps_by_iteration (scipy curve_fit, one host core) timed on 3 of the same curves; "
+                         "results agree to 5e-6 relative (scipy's stopping tolerance)"}
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -469,7 +498,7 @@ def run_b200(args, rank, world, local_rank):
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
         "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": config,
         "cells_per_s": value * n_genes * n, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
-        "gpu_launches": int(launches), "clocks": clocks, "host_rng_s_for_perms": host_rng_s, "api": api,
+        "gpu_launches": int(launches), "clocks": clocks, "host_rng_s_for_perms": host_rng_s, "api": api, "heaps": heaps,
     }
     emit(line)
     if world > 1:

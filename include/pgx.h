@@ -12,6 +12,7 @@
  *                                called from the L-BFGS-B lambdas at :156-160
  *   pgx_legacy_shuffles          replaces the np.arange + np.random.shuffle pair at :84-85
  *                                (numpy legacy MT19937 stream, bit-exact)
+ *   pgx_heaps_fit                batched counterpart of __fit_heaps_single__ (:39-48)
  *
  * Conventions: every function returns 0 on success and a non-zero code otherwise;
  * pgx_last_error() then returns a thread-local message.  No C++ types, exceptions or
@@ -135,6 +136,19 @@ int pgx_bernoulli_ll_grad(const uint32_t *d_xbits, int64_t words_per_row, int64_
                           int64_t n_genomes, const int32_t *d_row_count,
                           const int32_t *d_col_count, const double *d_p, const double *d_q,
                           double *d_ll, double *d_grad, void *d_scratch, void *stream);
+
+/* Batched Heaps-law fits y = kappa * x^alpha, x = 1 .. n_points, one per curve: the GPU counterpart of
+ * fit_heaps_by_iteration / __fit_heaps_single__ (pangenome_analysis.py:24-48; scipy curve_fit, start point
+ * alpha = 0.5, kappa = min(y)).  Levenberg-Marquardt with the analytic Jacobian, run to fp64 convergence.
+ *   d_curves : n_curves rows of ``stride`` elements, int32 (is_f64 == 0) or float64; the first n_points
+ *              of every row are fitted (the Pan half of a pgx_pan_core_curves row: stride = 2N)
+ *   d_fit    : [n_curves][2] float64 {alpha, kappa}
+ *   d_info   : optional [n_curves] int32, LM trials used (negative: stopped without converging)
+ *   d_scratch: pgx_heaps_scratch_bytes(n_points) bytes
+ * Deterministic.  Asynchronous on ``stream``. */
+size_t pgx_heaps_scratch_bytes(int64_t n_points);
+int pgx_heaps_fit(const void *d_curves, int32_t is_f64, int64_t n_curves, int64_t n_points, int64_t stride,
+                  double *d_fit, int32_t *d_info, void *d_scratch, void *stream);
 
 /* numpy legacy RandomState stream (host): ``count`` consecutive
  * ``a = np.arange(n); np.random.shuffle(a)`` results as uint16 rows, continuing from the

@@ -251,6 +251,35 @@ class PanCoreEngine:
         return out
 
 
+def fit_heaps_device(curves, n_points=None):
+    """Heaps-law fits of every row of a CUDA tensor of curves (int32 or float64, contiguous rows).
+
+    curves: [n_curves, stride]; the first ``n_points`` entries of each row are fitted (default: the
+    first half, i.e. the Pan half of a pan/core table).  Returns (fit float64 [n_curves, 2]
+    {alpha, kappa}, info int32 [n_curves]) as CUDA tensors; asynchronous on the current stream.
+    """
+    torch = _torch()
+    if not curves.is_cuda or curves.dim() != 2 or not curves.is_contiguous():
+        raise ValueError("curves must be a contiguous 2-D CUDA tensor")
+    if curves.dtype not in (torch.int32, torch.float64):
+        raise ValueError("curves must be int32 or float64")
+    n_curves, stride = int(curves.shape[0]), int(curves.shape[1])
+    n_points = stride // 2 if n_points is None else int(n_points)
+    if n_points < 1 or n_points > stride:
+        raise ValueError("n_points out of range")
+    lib = _native.load()
+    fit = torch.empty((n_curves, 2), dtype=torch.float64, device=curves.device)
+    info = torch.empty((n_curves,), dtype=torch.int32, device=curves.device)
+    scratch = torch.empty((int(lib.pgx_heaps_scratch_bytes(n_points)) + 7) // 8, dtype=torch.float64,
+                          device=curves.device)
+    with torch.cuda.device(curves.device):
+        _native.check(lib.pgx_heaps_fit(
+            curves.data_ptr(), 1 if curves.dtype == torch.float64 else 0, n_curves, n_points, stride,
+            fit.data_ptr(), info.data_ptr(), scratch.data_ptr(),
+            torch.cuda.current_stream(curves.device).cuda_stream))
+    return fit, info
+
+
 class BernoulliGrid:
     """Dense 0/1 gene x genome table, bit-packed on the GPU, for LL / gradient evaluations
     (pangenome_analysis.py:244-266)."""

@@ -250,6 +250,58 @@ def test_estimate_blocks_progress_and_rng_state(engine_mod, capsys):
 
 
 # ---------------------------------------------------------------------------------------
+# Batched Heaps-law fits
+# ---------------------------------------------------------------------------------------
+# scipy's curve_fit stops at ftol = xtol = 1.49e-8 and lands within ~1e-6 relative of the least-squares
+# optimum (1.3e-6 on the 5-point KAT); the GPU fit runs to fp64 convergence.
+HEAPS_RTOL = 5e-6
+
+
+@pytest.mark.parametrize("name", ["kat_6x5", "synth_800x50_s0", "c1_8000x50", "c2slice_4000x400"])
+def test_heaps_fits_match_reference_fixtures(engine_mod, name):
+    """pgx_heaps_fit against the alpha/kappa the live reference (scipy curve_fit) produced."""
+    import torch
+    from pangenomix_b200 import pangenome_analysis as pa
+    g = load_golden(name)
+    n = int(g["shape"][1])
+    curves = torch.from_numpy(np.ascontiguousarray(g["curves"].astype(np.int32))).cuda()
+    fit, info = engine_mod.fit_heaps_device(curves)
+    fit, info = fit.cpu().numpy(), info.cpu().numpy()
+    assert np.all(info > 0)
+    k = g["heaps_iter"].shape[0]
+    np.testing.assert_allclose(fit[:k], g["heaps_iter"], rtol=HEAPS_RTOL)
+    # float64 input, the mean row, DataFrame wrapper with the reference's labels
+    df = pd.DataFrame(g["curves"].astype(np.float64), index=["Iter%d" % (i + 1) for i in range(g["curves"].shape[0])],
+                      columns=["Pan%d" % (i + 1) for i in range(n)] + ["Core%d" % (i + 1) for i in range(n)])
+    got = pa.fit_heaps_by_iteration_gpu(df)
+    assert list(got.columns) == ["alpha", "kappa"] and list(got.index) == list(df.index)
+    np.testing.assert_allclose(got.values[:k], g["heaps_iter"], rtol=HEAPS_RTOL)
+    mean = pd.DataFrame([df.mean()], columns=df.columns)
+    np.testing.assert_allclose(pa.fit_heaps_by_iteration_gpu(mean).values[0], g["heaps_mean"], rtol=HEAPS_RTOL)
+    # bit-reproducible
+    fit2, _ = engine_mod.fit_heaps_device(curves)
+    assert np.array_equal(fit2.cpu().numpy(), fit)
+
+
+def test_heaps_fits_of_a_whole_table_against_scipy(engine_mod):
+    """Every iteration of a 400-genome table (200 curves): the drop-in scipy path on the host is the checker."""
+    import torch
+    from pangenomix_b200 import pangenome_analysis as pa, synth
+    coo = synth.bernoulli_matrix(4000, 400, 450, seed=20242)
+    eng = engine_mod.PanCoreEngine(coo)
+    np.random.seed(3)
+    perms = engine_mod.draw_legacy_permutations(400, 200)
+    d_curves = eng.curves_device(torch.from_numpy(perms.view(np.int16)).cuda())
+    fit, info = engine_mod.fit_heaps_device(d_curves)
+    assert int(info.min()) > 0
+    curves = d_curves.cpu().numpy().astype(np.float64)
+    df = pd.DataFrame(curves, index=["Iter%d" % (i + 1) for i in range(200)],
+                      columns=["Pan%d" % (i + 1) for i in range(400)] + ["Core%d" % (i + 1) for i in range(400)])
+    want = pa.fit_heaps_by_iteration(df.iloc[::10])
+    np.testing.assert_allclose(fit.cpu().numpy()[::10], want.values, rtol=HEAPS_RTOL)
+
+
+# ---------------------------------------------------------------------------------------
 # Bernoulli grid
 # ---------------------------------------------------------------------------------------
 def test_bernoulli_ll_grad_fixtures(engine_mod):
