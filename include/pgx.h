@@ -111,6 +111,16 @@ int pgx_pan_core_curves_f64(const pgx_plan *plan, const uint16_t *d_perms, int64
 int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int64_t n_perm,
                              void *h_curves, int32_t out_f64, int64_t perms_per_block);
 
+/* estimate_pan_core_size in one call (pangenome_analysis.py:76-90): draws n_iter consecutive
+ * ``np.arange(N); np.random.shuffle`` permutations from the numpy-legacy MT19937 state
+ * (mt_key[624] / mt_pos as np.random.get_state() reports them; advanced in place exactly as the
+ * reference's loop advances the global stream), rarefies them on the current device and writes
+ * the float64 [n_iter][2N] table the reference builds with np.hstack (:97) into h_curves
+ * (ordinary host memory).  RNG, H2D, kernels, D2H and the final copy are pipelined over three
+ * internal slots; staging is cached for the life of the library.  One call at a time per process. */
+int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_pos, int64_t n_iter,
+                          double *h_curves, int64_t perms_per_block);
+
 /* Launch-shape overrides for experiments (0 = heuristic): permutations per CTA of the list
  * kernel (1, 2, 4 or 8), row splits per permutation batch and threads per CTA. */
 int pgx_set_tuning(int32_t perms_per_cta, int32_t row_splits, int32_t threads_per_cta);

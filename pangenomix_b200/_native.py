@@ -17,7 +17,7 @@ EXPORTS = (
     "pgx_pan_core_curves_f64", "pgx_pan_core_curves_host", "pgx_set_tuning",
     "pgx_launch_count", "pgx_bernoulli_scratch_bytes", "pgx_bernoulli_ll_grad",
     "pgx_legacy_shuffles", "pgx_profile_enable", "pgx_profile_read",
-    "pgx_heaps_scratch_bytes", "pgx_heaps_fit",
+    "pgx_heaps_scratch_bytes", "pgx_heaps_fit", "pgx_estimate_pan_core",
 )
 
 
@@ -84,6 +84,8 @@ def load():
     lib.pgx_bernoulli_scratch_bytes.argtypes = [i64, i64]
     lib.pgx_bernoulli_ll_grad.restype = ctypes.c_int
     lib.pgx_bernoulli_ll_grad.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.pgx_estimate_pan_core.restype = ctypes.c_int
+    lib.pgx_estimate_pan_core.argtypes = [plan_p, vp, ctypes.POINTER(i32), i64, vp, i64]
     lib.pgx_heaps_scratch_bytes.restype = ctypes.c_size_t
     lib.pgx_heaps_scratch_bytes.argtypes = [i64]
     lib.pgx_heaps_fit.restype = ctypes.c_int

@@ -25,8 +25,13 @@
 // Kernel 3 (scan_kernel): adds the closed-form gene classes and turns each histogram into
 //   its curve with a block-wide prefix scan, in place.
 #include <stdlib.h>
+#include <string.h>
+#include <sys/mman.h>
+#include <unistd.h>
 
+#include <condition_variable>
 #include <mutex>
+#include <thread>
 #include <vector>
 
 #include "pgx_common.cuh"
@@ -486,7 +491,7 @@ int aux_for_device(Aux **out)
 
 template <typename OutT>
 int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, int32_t *d_hist,
-               OutT *d_out, cudaStream_t stream)
+               OutT *d_out, cudaStream_t stream, Aux *own_aux = nullptr)
 {
     if (int rc = check_plan(plan)) return rc;
     if (n_perm < 0) return fail(PGX_ERR_INVALID, "n_perm < 0");
@@ -507,10 +512,12 @@ int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, 
     }
     // The two row kernels only add into the histogram, in any order: unless per-kernel timing is
     // on (or PGX_NO_OVERLAP is set), the probe kernel runs beside the list kernel on a second stream.
-    Aux *aux = nullptr;
+    Aux *aux = own_aux;
     const bool overlap = !profile && !g_no_overlap && plan->n_tasks > 0 && plan->n_long > 0;
     if (overlap) {
-        if (int rc = aux_for_device(&aux)) return rc;
+        if (!aux) {
+            if (int rc = aux_for_device(&aux)) return rc;
+        }
         PGX_CUDA(cudaEventRecord(aux->fork, stream));
         PGX_CUDA(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
     }
@@ -658,6 +665,171 @@ int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int6
 #undef PGX_TRY
     cleanup();
     return PGX_OK;
+}
+
+// estimate_pan_core_size in one call (pangenome_analysis.py:76-90): RNG stream, upload, kernels,
+// download.  Three slots of pinned staging + device buffers (cached per device for the life of the
+// library); a producer thread draws the shuffles of a block and enqueues its H2D copy, kernels and
+// D2H copy, the calling thread waits for finished blocks in order and moves them into the caller's
+// (ordinary, pageable) result.
+namespace pgx {
+namespace {
+
+struct EstimateSlot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    Aux aux;                          // second stream + fork/join events of this slot's kernels
+    uint16_t *h_perm = nullptr, *d_perm = nullptr;
+    int32_t *d_hist = nullptr;
+    double *d_out = nullptr, *h_out = nullptr;
+};
+
+struct EstimateBuffers {
+    int device = -1;
+    long long block = 0, n = 0;
+    EstimateSlot slot[3];
+};
+
+void release(EstimateBuffers &b)
+{
+    for (auto &s : b.slot) {
+        if (s.h_perm) cudaFreeHost(s.h_perm);
+        if (s.h_out) cudaFreeHost(s.h_out);
+        if (s.d_perm) cudaFree(s.d_perm);
+        if (s.d_hist) cudaFree(s.d_hist);
+        if (s.d_out) cudaFree(s.d_out);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.aux.stream) cudaStreamDestroy(s.aux.stream);
+        if (s.aux.fork) cudaEventDestroy(s.aux.fork);
+        if (s.aux.join) cudaEventDestroy(s.aux.join);
+        s = EstimateSlot{};
+    }
+    b.device = -1;
+    b.block = b.n = 0;
+}
+
+int acquire(EstimateBuffers &b, int device, long long block, long long n)
+{
+    if (b.device == device && b.n == n && b.block >= block) return PGX_OK;
+    release(b);
+    for (auto &s : b.slot) {
+        PGX_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        PGX_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        PGX_CUDA(cudaStreamCreateWithFlags(&s.aux.stream, cudaStreamNonBlocking));
+        PGX_CUDA(cudaEventCreateWithFlags(&s.aux.fork, cudaEventDisableTiming));
+        PGX_CUDA(cudaEventCreateWithFlags(&s.aux.join, cudaEventDisableTiming));
+        s.aux.device = device;
+        PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s.h_perm), sizeof(uint16_t) * block * n, cudaHostAllocDefault));
+        PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s.h_out), sizeof(double) * block * 2 * n, cudaHostAllocDefault));
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_perm), sizeof(uint16_t) * block * n));
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_hist), sizeof(int32_t) * block * 2 * n));
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_out), sizeof(double) * block * 2 * n));
+    }
+    b.device = device;
+    b.block = block;
+    b.n = n;
+    return PGX_OK;
+}
+
+std::mutex g_estimate_mu;          // one estimate call at a time per process (it owns the staging)
+EstimateBuffers g_estimate_buffers;
+
+}  // namespace
+}  // namespace pgx
+
+int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_pos, int64_t n_iter,
+                          double *h_curves, int64_t perms_per_block)
+{
+    if (int rc = pgx::check_plan(plan)) return rc;
+    if (n_iter < 0) return pgx::fail(PGX_ERR_INVALID, "n_iter < 0");
+    if (!mt_key || !mt_pos || (!h_curves && n_iter > 0)) return pgx::fail(PGX_ERR_INVALID, "null pointer");
+    if (n_iter == 0) return PGX_OK;
+    const long long n = plan->n_genomes;
+    long long block = perms_per_block;
+    if (block <= 0) block = std::max(32ll, std::min(4096ll, (32ll << 20) / (16 * n)));
+    std::lock_guard<std::mutex> lock(pgx::g_estimate_mu);
+    int dev = 0;
+    PGX_CUDA(cudaGetDevice(&dev));
+    pgx::EstimateBuffers &buf = pgx::g_estimate_buffers;
+    if (int rc = pgx::acquire(buf, dev, block, n)) return rc;
+    block = std::min<long long>(block, n_iter);
+    const long long n_blocks = (n_iter + block - 1) / block;
+    {
+        // The result is usually fresh memory: ask for huge pages so that filling it costs one page
+        // fault per 2 MB instead of one per 4 KB (a hint; ignored where THP is off).
+        const uintptr_t page = 2u << 20;
+        const uintptr_t lo = (reinterpret_cast<uintptr_t>(h_curves) + page - 1) & ~(page - 1);
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(h_curves) + sizeof(double) * 2ull * n * n_iter) & ~(page - 1);
+        if (hi > lo) madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
+    }
+
+    // producer -> consumer hand-off: ``issued`` blocks have their GPU work enqueued, ``retired`` blocks
+    // have been copied out; slot of block k is k % 3, reusable once block k - 3 retired
+    std::mutex mu;
+    std::condition_variable cv;
+    long long issued = 0, retired = 0;
+    int producer_rc = PGX_OK;
+    char producer_err[512] = "";
+    std::thread producer([&]() {
+        cudaSetDevice(dev);
+        for (long long k = 0; k < n_blocks; ++k) {
+            {
+                std::unique_lock<std::mutex> lk(mu);
+                cv.wait(lk, [&] { return retired + 3 > k; });
+            }
+            pgx::EstimateSlot &s = buf.slot[k % 3];
+            const long long p0 = k * block, cnt = std::min<long long>(block, n_iter - p0);
+            int rc = pgx_legacy_shuffles(mt_key, mt_pos, n, cnt, s.h_perm);
+            if (!rc && cudaMemcpyAsync(s.d_perm, s.h_perm, sizeof(uint16_t) * cnt * n, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
+                rc = pgx::fail(PGX_ERR_CUDA, "H2D copy of the permutations failed");
+            if (!rc) rc = pgx::run_curves<double>(plan, s.d_perm, cnt, s.d_hist, s.d_out, s.stream, &s.aux);
+            if (!rc && cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * cnt * 2 * n, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
+                rc = pgx::fail(PGX_ERR_CUDA, "D2H copy of the curves failed");
+            if (!rc && cudaEventRecord(s.done, s.stream) != cudaSuccess) rc = pgx::fail(PGX_ERR_CUDA, "event record failed");
+            {
+                std::lock_guard<std::mutex> lk(mu);
+                if (rc) {
+                    producer_rc = rc;
+                    snprintf(producer_err, sizeof(producer_err), "%s", pgx_last_error());   // thread-local text
+                }
+                issued = rc ? n_blocks : k + 1;
+            }
+            cv.notify_all();
+            if (rc) return;
+        }
+    });
+    int rc = PGX_OK;
+    for (long long k = 0; k < n_blocks; ++k) {
+        {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return issued > k; });
+            if (producer_rc) break;
+        }
+        pgx::EstimateSlot &s = buf.slot[k % 3];
+        const long long p0 = k * block, cnt = std::min<long long>(block, n_iter - p0);
+        if (cudaEventSynchronize(s.done) != cudaSuccess) {
+            rc = pgx::fail(PGX_ERR_CUDA, "a block of curves failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
+            std::lock_guard<std::mutex> lk(mu);
+            retired = n_blocks + 3;                     // let the producer run out
+            cv.notify_all();
+            break;
+        }
+        memcpy(h_curves + p0 * 2 * n, s.h_out, sizeof(double) * cnt * 2 * n);
+        {
+            std::lock_guard<std::mutex> lk(mu);
+            retired = k + 1;
+        }
+        cv.notify_all();
+    }
+    {
+        std::lock_guard<std::mutex> lk(mu);
+        retired = n_blocks + 3;
+    }
+    cv.notify_all();
+    producer.join();
+    if (producer_rc) return pgx::fail(producer_rc, "%s", producer_err);
+    return rc;
 }
 
 int pgx_profile_enable(int32_t on)

@@ -168,86 +168,40 @@ class PanCoreEngine:
         return out
 
     # ---- the reference's call: draw from np.random, return float64 (num_iter, 2N) -----
-    def _estimate_buffers(self, block):
-        """Staging of ``estimate``: two slots of pinned host + device buffers, kept across calls."""
-        torch = _torch()
-        cached = getattr(self, "_est", None)
-        if cached is not None and cached["block"] >= block:
-            return cached
-        n = self.n_genomes
-        with torch.cuda.device(self.device):
-            self._est = {
-                "block": block,
-                "streams": [torch.cuda.Stream(self.device) for _ in range(2)],
-                "h_perm": [pinned_empty((block, n), np.uint16) for _ in range(2)],
-                "h_out": [pinned_empty((block, 2 * n), np.float64) for _ in range(2)],
-                "d_perm": [torch.empty((block, n), dtype=torch.int16, device=self.device) for _ in range(2)],
-                "d_hist": [torch.empty((block, 2 * n), dtype=torch.int32, device=self.device) for _ in range(2)],
-                "d_out": [torch.empty((block, 2 * n), dtype=torch.float64, device=self.device) for _ in range(2)],
-            }
-        return self._est
-
     def estimate(self, num_iter, log_batch=-1, block=None):
-        """pangenome_analysis.py:76-90: curves for ``num_iter`` shuffles of the global RNG.
+        """pangenome_analysis.py:76-90: curves for ``num_iter`` shuffles of the global numpy RNG.
 
-        Blocks of permutations flow through two slots: while the GPU works on block k (H2D,
-        kernels, D2H into pinned staging), the host draws the shuffles of block k+1 and a helper
-        thread moves the finished curves of block k-1 into the (ordinary, pageable) result.
+        One C call (pgx_estimate_pan_core) per stretch of iterations: the library draws the shuffles
+        from the legacy MT19937 state, and pipelines RNG, H2D, kernels, D2H and the copy into the
+        (ordinary, pageable) float64 result over three internal slots.  With ``log_batch`` > 0 the
+        stretches end at the reference's progress lines (:82-83).
         """
-        import concurrent.futures
         torch = _torch()
         num_iter = int(num_iter)
         n = self.n_genomes
         out = np.empty((num_iter, 2 * n), dtype=np.float64)
         if num_iter == 0:
             return out
-        default_block = max(32, min(4096, (32 << 20) // (16 * n)))
-        block = default_block if block is None else max(1, int(block))
-        buf = self._estimate_buffers(max(block, default_block))       # sized once, reused by later calls
-        block = max(1, min(block, num_iter))
-        streams = buf["streams"]
-        done = [None, None]            # (event, first row, count) of the block in flight in each slot
-        copies = [None, None]          # future of the slot's last staging -> result copy
-
-        def retire(slot):
-            if done[slot] is None:
-                return
-            ev, p0, cnt = done[slot]
-            done[slot] = None
-
-            def move():
-                ev.synchronize()
-                np.copyto(out[p0:p0 + cnt], buf["h_out"][slot][0][:cnt])
-            copies[slot] = pool.submit(move)
-
-        with torch.cuda.device(self.device), concurrent.futures.ThreadPoolExecutor(max_workers=1) as pool:
-            slot = 0
-            for p0 in range(0, num_iter, block):
-                cnt = min(block, num_iter - p0)
-                if log_batch > 0:
-                    first = ((p0 + log_batch) // log_batch) * log_batch
-                    for it in range(first, p0 + cnt + 1, log_batch):
-                        print('\tIteration', it, 'of', num_iter)       # :82-83
-                if copies[slot] is not None:
-                    copies[slot].result()            # the slot's staging buffers are free again
-                    copies[slot] = None
-                host_perm, host_owner = buf["h_perm"][slot]
-                draw_legacy_permutations(n, cnt, out=host_perm[:cnt])
-                with torch.cuda.stream(streams[slot]):
-                    buf["d_perm"][slot][:cnt].copy_(host_owner[:cnt], non_blocking=True)
-                    _native.check(self.lib.pgx_pan_core_curves_f64(
-                        ctypes.byref(self.c_plan), buf["d_perm"][slot].data_ptr(), cnt,
-                        buf["d_hist"][slot].data_ptr(), buf["d_out"][slot].data_ptr(),
-                        streams[slot].cuda_stream))
-                    buf["h_out"][slot][1][:cnt].copy_(buf["d_out"][slot][:cnt], non_blocking=True)
-                    ev = torch.cuda.Event()
-                    ev.record(streams[slot])
-                done[slot] = (ev, p0, cnt)
-                retire(slot)                        # the helper waits for the GPU, then copies
-                slot ^= 1
-            for s in range(2):
-                if copies[s] is not None:
-                    copies[s].result()
+        state = np.random.get_state()
+        if os.environ.get("PGX_NUMPY_SHUFFLE") == "1" or state[0] != "MT19937":
+            perms = draw_legacy_permutations(n, num_iter)
+            return self.curves_host(perms, out=out, out_f64=True)
+        key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+        pos = ctypes.c_int32(int(state[2]))
+        stretch = num_iter if log_batch <= 0 else int(log_batch)
+        with torch.cuda.device(self.device):
+            p0 = 0
+            while p0 < num_iter:
+                cnt = min(stretch, num_iter - p0)
+                if log_batch > 0 and p0 > 0:
+                    print('\tIteration', p0, 'of', num_iter)       # :82-83
+                _native.check(self.lib.pgx_estimate_pan_core(
+                    ctypes.byref(self.c_plan), key.ctypes.data, ctypes.byref(pos), cnt,
+                    out[p0:].ctypes.data, int(block or 0)))
+                p0 += cnt
+            if log_batch > 0 and num_iter % log_batch == 0:
+                print('\tIteration', num_iter, 'of', num_iter)
+        np.random.set_state((state[0], key, int(pos.value), state[3], state[4]))
         return out
 
 
