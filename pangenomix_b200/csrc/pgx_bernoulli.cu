@@ -10,10 +10,12 @@
 // X is bit-packed (one bit per cell), so the kernel is fp64-ALU bound (one log and one
 // division per absent cell); the table stays L2-resident across optimiser iterations.
 //
-// grid_kernel: CTA (row tile, column tile of 512 genomes).  A lane owns 16 columns
-//   (j = col0 + 32 w + lane), keeps q_j and its dL/dq partial sums in registers, and the
-//   warps of the CTA walk the rows of the tile.  Row sums are combined with a fixed
-//   shuffle tree, column sums across warps through shared memory in warp order, so the
+// grid_kernel: CTA (row tile, column tile of 512 genomes); the warps of the CTA walk the rows
+//   of the tile.  For every row the warp compacts the absent columns of its 16 bitmap words
+//   into a shared-memory list (popcount prefix over the words) and then every lane evaluates
+//   one absent cell per step; dL/dq partial sums live in a per-warp shared-memory row (a
+//   column occurs once per row, so there are no collisions and the order is fixed).  Row sums
+//   use a fixed shuffle tree, column sums are combined across warps in warp order, so the
 //   result is bit-reproducible run to run.
 // finish_kernel: fixed-order reduction of the per-tile partials plus the closed-form terms.
 #include "pgx_common.cuh"
@@ -48,6 +50,8 @@ grid_kernel(const uint32_t *__restrict__ xbits, const BernoulliShape shape,
             double *__restrict__ ll_part)   // [row_tiles * col_tiles]
 {
     __shared__ double s_gq[BG_WARPS][BG_TILE_COLS];
+    __shared__ double s_q[BG_TILE_COLS];
+    __shared__ uint16_t s_cols[BG_WARPS][BG_TILE_COLS];     // per warp: the absent columns of its current row
     __shared__ double s_ll[BG_WARPS];
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -57,38 +61,53 @@ grid_kernel(const uint32_t *__restrict__ xbits, const BernoulliShape shape,
     const long long row_begin = static_cast<long long>(row_tile) * shape.rows_per_tile;
     const long long row_end = min(shape.n_genes, row_begin + shape.rows_per_tile);
 
-    double qj[BG_COLS_PER_LANE], gq[BG_COLS_PER_LANE];
-    uint32_t col_ok = 0;
+    for (int c = tid; c < BG_TILE_COLS; c += BG_THREADS) {
+        s_q[c] = col0 + c < shape.n_genomes ? q[col0 + c] : 0.0;
 #pragma unroll
-    for (int w = 0; w < BG_COLS_PER_LANE; ++w) {
-        const long long j = col0 + 32 * w + lane;
-        const bool ok = j < shape.n_genomes;
-        qj[w] = ok ? q[j] : 0.0;
-        gq[w] = 0.0;
-        col_ok |= static_cast<uint32_t>(ok) << w;
+        for (int w = 0; w < BG_WARPS; ++w) s_gq[w][c] = 0.0;
     }
+    __syncthreads();
     const int n_words = static_cast<int>(min(static_cast<long long>(BG_COLS_PER_LANE),
                                              shape.words_per_row - word0));
+    // columns of word ``lane`` that exist (the last word of a row may be ragged)
+    uint32_t valid = 0;
+    if (lane < n_words) {
+        const long long left = shape.n_genomes - (col0 + 32ll * lane);
+        valid = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+    }
+    uint16_t *cols = s_cols[warp];
+    double *gq = s_gq[warp];
 
     double ll = 0.0;
     for (long long i = row_begin + warp; i < row_end; i += BG_WARPS) {
         const double pi = p[i];
-        // lane w holds bitmap word w of this row's column tile
-        uint32_t my_word = 0xffffffffu;
-        if (lane < n_words) my_word = xbits[i * shape.words_per_row + word0 + lane];
-        double gp = 0.0;
+        // Only absent cells cost arithmetic (:248, :261-265 with the X = 1 cells in closed form) and
+        // they are few and scattered: compact them so that every lane works.  Lane w < 16 owns
+        // bitmap word w of this row's column tile and lists its absent columns at its offset.
+        uint32_t absent = 0;
+        if (lane < n_words) absent = ~xbits[i * shape.words_per_row + word0 + lane] & valid;
+        const int mine = __popc(absent);
+        int before = mine;
 #pragma unroll
-        for (int w = 0; w < BG_COLS_PER_LANE; ++w) {
-            const uint32_t word = __shfl_sync(FULL_MASK, my_word, w);
-            const bool absent = (((word >> lane) & 1u) == 0u) && ((col_ok >> w) & 1u);
-            if (absent) {
-                const double u = 1.0 - pi * qj[w];     // :261  nprobs = 1 - outer(P, Q)
-                ll += log(u);                          // :248  (1 - X) * log(1 - probs)
-                const double r = 1.0 / u;
-                gp += qj[w] * r;                       // :263
-                gq[w] += pi * r;                       // :265
-            }
+        for (int off = 1; off < 16; off <<= 1) {
+            const int v = __shfl_up_sync(FULL_MASK, before, off);
+            if (lane >= off) before += v;
         }
+        const int total = __shfl_sync(FULL_MASK, before, 15);
+        int at = before - mine;
+        for (uint32_t m = absent; m; m &= m - 1u) cols[at++] = static_cast<uint16_t>(32 * lane + __ffs(m) - 1);
+        __syncwarp();
+        double gp = 0.0;
+        for (int t = lane; t < total; t += 32) {
+            const int c = cols[t];
+            const double qj = s_q[c];
+            const double u = 1.0 - pi * qj;            // :261  nprobs = 1 - outer(P, Q)
+            ll += log(u);                              // :248  (1 - X) * log(1 - probs)
+            const double r = 1.0 / u;
+            gp += qj * r;                              // :263
+            gq[c] += pi * r;                           // :265  (one lane per column within a row)
+        }
+        __syncwarp();
         gp = warp_sum(gp);
         if (lane == 0) gp_part[static_cast<long long>(col_tile) * shape.n_genes + i] = gp;
         // closed-form term of the present cells of this gene, m_i log p_i, counted once (column tile 0)
@@ -96,8 +115,6 @@ grid_kernel(const uint32_t *__restrict__ xbits, const BernoulliShape shape,
     }
 
     // combine the warps' column sums in warp order
-#pragma unroll
-    for (int w = 0; w < BG_COLS_PER_LANE; ++w) s_gq[warp][32 * w + lane] = gq[w];
     ll = warp_sum(ll);
     if (lane == 0) s_ll[warp] = ll;
     __syncthreads();
