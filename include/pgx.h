@@ -57,9 +57,11 @@ enum {
  *                ordered inside a row so that neighbouring lanes gather from different
  *                shared-memory banks.  d_sorted_* hold the same lists plainly sorted.
  *  bitmap rows   The remaining (long) genes, as a genome-major bit-sliced bitmap: rows are
- *                grouped in superblocks of 1,024; d_bits[(sb * N + c) * 32 + w] holds, in bit b,
- *                the presence of row sb * 1024 + 32 w + b in genome c (one 128-byte line per
- *                (superblock, genome)).  Rows of similar density share a superblock.
+ *                grouped in superblocks of 1,024 W (W = slice_words = 1, 2 or 4);
+ *                d_bits[(sb * N + c) * 32 W + w] holds, in bit b, the presence of row
+ *                sb * 1024 W + 32 w + b in genome c (one line of 128 W bytes per (superblock,
+ *                genome); lane l of the probing warp owns words l W .. l W + W - 1).  Rows of
+ *                similar density share a superblock.
  */
 typedef struct pgx_plan {
     const uint16_t *d_chunks;      /* [n_chunks * 8] list rows, 16-byte aligned */
@@ -68,7 +70,7 @@ typedef struct pgx_plan {
                                       costly tasks first */
     const uint16_t *d_sorted_idx;  /* sorted copy of the list rows */
     const int32_t *d_sorted_ptr;   /* [n_rows + 1] offsets into d_sorted_idx */
-    const uint32_t *d_bits;        /* [n_superblocks * n_genomes * 32] bit-sliced bitmap rows, 16-byte aligned */
+    const uint32_t *d_bits;        /* [n_superblocks * n_genomes * 32 W] bit-sliced bitmap rows, 16-byte aligned */
     const void *reserved_ptr;
     const int32_t *d_colsum;       /* [n_genomes] #genes present in genome c (all genes of the table) */
     const int32_t *d_w_present;    /* [n_genomes] #genes present ONLY in genome c */
@@ -79,9 +81,9 @@ typedef struct pgx_plan {
     int32_t n_rows;                /* list rows */
     int32_t n_tasks;
     int32_t n_long;                /* bitmap rows */
-    int32_t n_superblocks;         /* ceil(n_long / 1024) */
+    int32_t n_superblocks;         /* ceil(n_long / (1024 * slice_words)) */
     int32_t perms_per_cta;         /* 8, 4, 2 or 1: rank tables that share a CTA's shared memory */
-    int32_t reserved;
+    int32_t slice_words;           /* W = 1, 2 or 4: words per lane of a (superblock, genome) line */
 } pgx_plan;
 
 int pgx_version(void);

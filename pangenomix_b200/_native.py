@@ -45,7 +45,7 @@ class PgxPlan(ctypes.Structure):
         ("n_long", ctypes.c_int32),
         ("n_superblocks", ctypes.c_int32),
         ("perms_per_cta", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("slice_words", ctypes.c_int32),
     ]
 
 

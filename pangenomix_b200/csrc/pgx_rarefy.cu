@@ -247,64 +247,111 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
 }
 
 // Bitmap rows, bit-sliced: 32 genes per word, genome-major.  A warp owns one superblock of
-// 1,024 bitmap rows and one permutation; lane l holds rows 32 l .. 32 l + 31 of the
-// superblock as one word.  Walking the genome order, step k loads ONE coalesced 128-byte line
-// -- the presence bits of all 1,024 genes in genome perm[k] -- and
+// 1,024 W bitmap rows (W = 1, 2 or 4 words per lane) and one permutation; lane l holds rows
+// 32 W l .. 32 W l + 32 W - 1 of the superblock as W words.  Walking the genome order, step k
+// loads ONE coalesced line of 128 W bytes -- the presence bits of all 1,024 W genes in genome
+// perm[k] -- and
 //     flipped = (line ^ line_of_rank_0) & pending
 // marks the genes whose bit differs from the rank-0 genome's for the first time: k is their
 // statistic (first presence if the rank-0 bit was 0, first absence if it was 1).  The walk
 // stops when no gene of the superblock is pending: O(N / m) steps of O(1) work per 32 genes,
 // the reference's own genome-by-genome accumulation (:87-:90) restricted to unresolved genes.
 constexpr int SLICE_WARPS = 4;
-constexpr int SLICE_DEPTH = 8;         // lines in flight per warp
 
+template <int W>
+struct SliceVec;
+template <>
+struct SliceVec<1> { using type = uint32_t; };
+template <>
+struct SliceVec<2> { using type = uint2; };
+template <>
+struct SliceVec<4> { using type = uint4; };
+
+template <int W>
+__device__ __forceinline__ void load_line(const uint32_t *p, uint32_t (&w)[W])
+{
+    const typename SliceVec<W>::type v = __ldg(reinterpret_cast<const typename SliceVec<W>::type *>(p));
+    if constexpr (W == 1) {
+        w[0] = v;
+    } else if constexpr (W == 2) {
+        w[0] = v.x;
+        w[1] = v.y;
+    } else {
+        w[0] = v.x;
+        w[1] = v.y;
+        w[2] = v.z;
+        w[3] = v.w;
+    }
+}
+
+template <int W>
 __global__ void __launch_bounds__(SLICE_WARPS * 32, 8)
 probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long long n_perm,
              int32_t *__restrict__ hist)
 {
+    constexpr int DEPTH = W == 4 ? 4 : 8;          // lines in flight per warp
     const int n = plan.n_genomes;
     const int lane = threadIdx.x & 31;
     const long long unit = static_cast<long long>(blockIdx.x) * SLICE_WARPS + (threadIdx.x >> 5);
     if (unit >= n_perm * plan.n_superblocks) return;           // whole warps leave together
     const long long sb = unit / n_perm, q = unit - sb * n_perm;   // costly superblocks first
 
-    const uint32_t *__restrict__ lines = plan.d_bits + (static_cast<size_t>(sb) * n) * 32 + lane;
+    const uint32_t *__restrict__ lines = plan.d_bits + (static_cast<size_t>(sb) * n) * (32 * W) + lane * W;
     const uint16_t *__restrict__ perm = perms + q * n;
     int32_t *out = hist + q * 2ll * n + (lane == 1 ? n : 0);      // lane 0 adds pan counts, lane 1 core counts
 
-    const long long first_row = sb * 1024 + lane * 32;
-    const long long left = static_cast<long long>(plan.n_long) - first_row;
-    uint32_t pending = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
-    const uint32_t b0 = __ldg(lines + static_cast<size_t>(perm[0]) * 32);
-
+    uint32_t pending[W], b0[W];
+#pragma unroll
+    for (int j = 0; j < W; ++j) {
+        const long long left = static_cast<long long>(plan.n_long) - (sb * (1024 * W) + (lane * W + j) * 32);
+        pending[j] = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
+    }
     const uint32_t genome0 = perm[0];
+    load_line<W>(lines + static_cast<size_t>(genome0) * (32 * W), b0);
+
     for (int k0 = 0; k0 < n; k0 += 32) {
         // genomes of ranks k0 .. k0 + 31; ranks past the end repeat the rank-0 genome (never a flip)
         const uint32_t chunk = k0 + lane < n ? perm[k0 + lane] : genome0;
 #pragma unroll 1
-        for (int j0 = 0; j0 < 32; j0 += SLICE_DEPTH) {
-            uint32_t d[SLICE_DEPTH];
+        for (int j0 = 0; j0 < 32; j0 += DEPTH) {
+            uint32_t d[DEPTH][W];
             uint32_t any = 0;
 #pragma unroll
-            for (int j = 0; j < SLICE_DEPTH; ++j) {
+            for (int j = 0; j < DEPTH; ++j) {
                 const uint32_t c = __shfl_sync(FULL_MASK, chunk, j0 + j);
-                d[j] = __ldg(lines + static_cast<size_t>(c) * 32) ^ b0;
-                any |= d[j];
-            }
-            // late in the walk few genes are pending and most groups of 8 genomes flip none
-            if (!__any_sync(FULL_MASK, any & pending)) continue;
+                load_line<W>(lines + static_cast<size_t>(c) * (32 * W), d[j]);
 #pragma unroll
-            for (int j = 0; j < SLICE_DEPTH; ++j) {
-                const uint32_t flipped = d[j] & pending;
-                if (!__any_sync(FULL_MASK, flipped)) continue;      // mid / late walk: most single steps flip nothing
-                pending &= ~flipped;
+                for (int x = 0; x < W; ++x) {
+                    d[j][x] ^= b0[x];
+                    any |= d[j][x] & pending[x];
+                }
+            }
+            // late in the walk few genes are pending and most groups of genomes flip none
+            if (!__any_sync(FULL_MASK, any)) continue;
+#pragma unroll
+            for (int j = 0; j < DEPTH; ++j) {
+                uint32_t flipped[W], some = 0;
+#pragma unroll
+                for (int x = 0; x < W; ++x) {
+                    flipped[x] = d[j][x] & pending[x];
+                    some |= flipped[x];
+                }
+                if (!__any_sync(FULL_MASK, some)) continue;        // mid / late walk: most single steps flip nothing
                 // low half: genes first seen at k (pan side); high half: genes first missed at k (core side)
-                const uint32_t packed = __popc(flipped & ~b0) | (__popc(flipped & b0) << 16);
-                const uint32_t total = __reduce_add_sync(FULL_MASK, packed);
+                uint32_t packed = 0;
+#pragma unroll
+                for (int x = 0; x < W; ++x) {
+                    pending[x] &= ~flipped[x];
+                    packed += __popc(flipped[x] & ~b0[x]) | (__popc(flipped[x] & b0[x]) << 16);
+                }
+                const uint32_t total = __reduce_add_sync(FULL_MASK, packed);     // <= 4,096 per half
                 const uint32_t mine = lane == 1 ? total >> 16 : total & 0xffffu;
                 if (lane < 2 && mine) atomicAdd(out + (k0 + j0 + j), static_cast<int>(mine));
             }
-            if (!__any_sync(FULL_MASK, pending)) return;
+            uint32_t left = 0;
+#pragma unroll
+            for (int x = 0; x < W; ++x) left |= pending[x];
+            if (!__any_sync(FULL_MASK, left)) return;
         }
     }
 }
@@ -393,8 +440,10 @@ int check_plan(const pgx_plan *plan)
         return fail(PGX_ERR_INVALID, "plan has list tasks but null list arrays");
     if (plan->n_long > 0 && !plan->d_bits)
         return fail(PGX_ERR_INVALID, "plan has bitmap rows but a null bitmap");
-    if (plan->n_superblocks != (plan->n_long + 1023) / 1024)
-        return fail(PGX_ERR_INVALID, "n_superblocks must be ceil(n_long / 1024)");
+    if (plan->n_long > 0 && plan->slice_words != 1 && plan->slice_words != 2 && plan->slice_words != 4)
+        return fail(PGX_ERR_INVALID, "slice_words must be 1, 2 or 4");
+    if (plan->n_long > 0 && plan->n_superblocks != (plan->n_long + 1024 * plan->slice_words - 1) / (1024 * plan->slice_words))
+        return fail(PGX_ERR_INVALID, "n_superblocks must be ceil(n_long / (1024 * slice_words))");
     if ((reinterpret_cast<uintptr_t>(plan->d_chunks) | reinterpret_cast<uintptr_t>(plan->d_tasks) |
          reinterpret_cast<uintptr_t>(plan->d_bits)) & 15)
         return fail(PGX_ERR_INVALID, "d_chunks, d_tasks and d_bits must be 16-byte aligned");
@@ -460,7 +509,11 @@ int launch_probe(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm
     const long long units = n_perm * plan.n_superblocks;
     const long long blocks = (units + SLICE_WARPS - 1) / SLICE_WARPS;
     if (blocks > 2147483647ll) return fail(PGX_ERR_UNSUPPORTED, "too many (superblock, permutation) units in one call");
-    probe_kernel<<<static_cast<unsigned>(blocks), SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, d_hist);
+    switch (plan.slice_words) {
+        case 4: probe_kernel<4><<<static_cast<unsigned>(blocks), SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, d_hist); break;
+        case 2: probe_kernel<2><<<static_cast<unsigned>(blocks), SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, d_hist); break;
+        default: probe_kernel<1><<<static_cast<unsigned>(blocks), SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, d_hist); break;
+    }
     PGX_LAUNCH_CHECK("probe_kernel");
     return PGX_OK;
 }

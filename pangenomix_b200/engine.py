@@ -95,7 +95,8 @@ class PanCoreEngine:
         if host_plan is None:
             if long_threshold is None and os.environ.get("PGX_LONG_THRESHOLD"):
                 long_threshold = int(os.environ["PGX_LONG_THRESHOLD"])
-            host_plan = build_host_plan(data, long_threshold=long_threshold)
+            slice_words = int(os.environ["PGX_SLICE_WORDS"]) if os.environ.get("PGX_SLICE_WORDS") else None
+            host_plan = build_host_plan(data, long_threshold=long_threshold, slice_words=slice_words)
         self.host_plan = host_plan
         hp = self.host_plan
         self.n_genes, self.n_genomes = hp.n_genes, hp.n_genomes
@@ -119,7 +120,7 @@ class PanCoreEngine:
             d_colsum=ptr["colsum"], d_w_present=ptr["w_present"], d_w_absent=ptr["w_absent"],
             n_chunks=hp.n_chunks, n_genomes=hp.n_genomes, n_genes=hp.n_genes,
             n_rows=hp.n_rows, n_tasks=hp.n_tasks, n_long=hp.n_long,
-            n_superblocks=hp.n_superblocks, perms_per_cta=hp.perms_per_cta, reserved=0)
+            n_superblocks=hp.n_superblocks, perms_per_cta=hp.perms_per_cta, slice_words=hp.slice_words)
 
     # ---- device-resident path -------------------------------------------------------
     def curves_device(self, perms, out=None):

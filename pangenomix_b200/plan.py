@@ -18,8 +18,8 @@ Three populations of genes (include/pgx.h describes the device side):
                     the entries of every row ordered so that the lanes of a shared-memory
                     bank group hit distinct banks of the rank table.
 * bitmap rows    -- the remaining (long) genes as a genome-major bit-sliced bitmap (32 genes per
-                    word, 1,024 per 128-byte line); the probe kernel walks genomes in rank order
-                    for 1,024 genes at once instead of scanning long lists.
+                    word, 1,024 W per 128 W-byte line, W = 1, 2 or 4); the probe kernel walks genomes in
+                    rank order for 1,024 W genes at once instead of scanning long lists.
 
 Everything here is numpy on the host, runs once per matrix ("uploaded once"), and is
 O(nnz).  No compute of curves happens here.
@@ -34,7 +34,14 @@ import scipy.sparse
 MAX_GENOMES = 65503          # genome indices, ranks and the 32 sentinel indices N..N+31 are uint16
 CHUNK = 8                    # indices per 16-byte chunk
 SENTINELS = 32               # rank-table rows N..N+31 hold 0xffff
-SUPERBLOCK = 1024            # bitmap rows per (superblock, genome) line of 128 bytes
+SLICE_ROWS = 1024            # bitmap rows per 128 bytes of a (superblock, genome) line: 32 lanes x 32 bits
+
+
+def slice_words_for(n_long):
+    """Words per lane of the probe walk (1, 2 or 4): wider lines amortise the per-step instructions over
+    more genes, as long as (superblocks x permutations) still fills the GPU with warps."""
+    return 4 if n_long >= 32768 else (2 if n_long >= 8192 else 1)
+
 RUN_LANE_CHUNKS = 32         # most chunk iterations a warp streams per task (sub-blocks of 32 rows x chunks per row)
 COLOUR_MAX_CHUNKS = 32       # rows of more chunks than this use the cheap positional bank ordering
 RUN_TARGET_TASKS = 1024      # ... but small tables keep enough tasks to spread over the warps of a CTA row
@@ -85,7 +92,8 @@ class HostPlan:
     row_len: np.ndarray       # int32  [n_rows] folded list length
     row_absent: np.ndarray    # bool   [n_rows] True when the list holds ABSENT genomes
     # bitmap rows
-    bits: np.ndarray          # uint32 [n_superblocks * N * 32]  bit b of word (sb, c, w) = row 1024 sb + 32 w + b in genome c
+    bits: np.ndarray          # uint32 [n_superblocks * N * 32 W]  bit b of word (sb, c, w) = row 1024 W sb + 32 w + b in genome c
+    slice_words: int          # W: words per lane of a (superblock, genome) line (1, 2 or 4)
     long_gene: np.ndarray     # int64  [n_long]
     nnz_list: int = 0         # present entries of the list-row genes (roofline apportioning)
     nnz_long: int = 0         # present entries of the bitmap-row genes
@@ -100,7 +108,8 @@ class HostPlan:
 
     @property
     def n_superblocks(self):
-        return (self.n_long + SUPERBLOCK - 1) // SUPERBLOCK
+        rows = SLICE_ROWS * self.slice_words
+        return (self.n_long + rows - 1) // rows
 
     @property
     def n_tasks(self):
@@ -338,7 +347,7 @@ def _bank_ordered_chunks(flat, ptr, block_first, block_nch, block_first_row, blo
     return chunks
 
 
-def build_host_plan(data, long_threshold=None, perms_per_cta=None) -> HostPlan:
+def build_host_plan(data, long_threshold=None, perms_per_cta=None, slice_words=None) -> HostPlan:
     csr = gene_major_csr(data)
     n_genes, n = csr.shape
     if n < 1:
@@ -385,17 +394,21 @@ def build_host_plan(data, long_threshold=None, perms_per_cta=None) -> HostPlan:
 
     # ---- bitmap rows: genome-major, bit-sliced, superblocks of 1,024 rows of similar density ----
     long_gene = genes[is_long]
-    n_super = (long_gene.size + SUPERBLOCK - 1) // SUPERBLOCK
+    slice_words = slice_words_for(long_gene.size) if slice_words is None else int(slice_words)
+    if slice_words not in (1, 2, 4):
+        raise ValueError("slice_words must be 1, 2 or 4")
+    sb_rows = SLICE_ROWS * slice_words
+    n_super = (long_gene.size + sb_rows - 1) // sb_rows
     if long_gene.size:
         m_long = m[long_gene]
         order = np.argsort(np.minimum(m_long, n - m_long), kind="stable")   # longest walks first
         long_gene = long_gene[order]
-        bits = np.zeros((n_super, n, SUPERBLOCK // 32), dtype=np.uint32)
+        bits = np.zeros((n_super, n, sb_rows // 32), dtype=np.uint32)
         for sb in range(n_super):
-            rows = long_gene[sb * SUPERBLOCK:(sb + 1) * SUPERBLOCK]
+            rows = long_gene[sb * sb_rows:(sb + 1) * sb_rows]
             lens = m[rows]
             src = np.repeat(indptr[rows], lens) + _segment_positions(lens)
-            dense = np.zeros((n, SUPERBLOCK), dtype=bool)                    # [genome][row in superblock]
+            dense = np.zeros((n, sb_rows), dtype=bool)                       # [genome][row in superblock]
             dense[indices[src], np.repeat(np.arange(rows.size), lens)] = True
             bits[sb] = np.packbits(dense, axis=1, bitorder="little").view(np.uint32)
         bits = bits.reshape(-1)
@@ -462,5 +475,5 @@ def build_host_plan(data, long_threshold=None, perms_per_cta=None) -> HostPlan:
         chunks=chunks, tasks=np.ascontiguousarray(tasks),
         sorted_idx=flat.astype(np.uint16), sorted_ptr=ptr.astype(np.int32),
         row_gene=genes, row_len=length.astype(np.int32), row_absent=use_abs.astype(bool),
-        bits=bits, long_gene=long_gene,
+        bits=bits, slice_words=slice_words, long_gene=long_gene,
         nnz_list=int(m[genes].sum()), nnz_long=int(m[long_gene].sum()))

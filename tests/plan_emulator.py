@@ -74,7 +74,8 @@ def curves_from_plan(hp, perms, hist_bins=None):
     n_perm = perms.shape[0]
     out = np.zeros((n_perm, 2 * n), dtype=np.int64)
     rows = list(list_rows(hp))
-    bits = hp.bits.reshape(hp.n_superblocks, n, 32) if hp.n_long else None
+    words = 32 * hp.slice_words
+    bits = hp.bits.reshape(hp.n_superblocks, n, words) if hp.n_long else None
     for p in range(n_perm):
         perm = perms[p]
         table = np.full(n + 32, 0xFFFF, dtype=np.int64)
@@ -91,12 +92,12 @@ def curves_from_plan(hp, perms, hist_bins=None):
                 k = _mex_probe(perm, lst, n)
                 assert k < n
                 hist[other_off + k] += 1
-        # probe kernel: walk the genome order for a superblock of 1,024 rows at once; a row's
+        # probe kernel: walk the genome order for a superblock of 1,024 W rows at once; a row's
         # statistic is the first rank whose bit differs from the rank-0 genome's bit
         for sb in range(hp.n_superblocks):
-            rows_here = min(1024, hp.n_long - sb * 1024)
-            pending = np.zeros(32, dtype=np.uint32)
-            for w in range(32):
+            rows_here = min(32 * words, hp.n_long - sb * 32 * words)
+            pending = np.zeros(words, dtype=np.uint32)
+            for w in range(words):
                 left = rows_here - 32 * w
                 pending[w] = 0xFFFFFFFF if left >= 32 else ((1 << left) - 1 if left > 0 else 0)
             b0 = bits[sb, perm[0]]

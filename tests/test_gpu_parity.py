@@ -112,8 +112,20 @@ def test_bitmap_probe_rows(engine_mod, threshold):
     eng = engine_mod.PanCoreEngine(coo, long_threshold=threshold)
     hp = eng.host_plan
     assert hp.n_long > 0 and (threshold > 2 or hp.n_rows == 0)
-    assert hp.n_superblocks == (hp.n_long + 1023) // 1024
+    assert hp.n_superblocks == (hp.n_long + 1024 * hp.slice_words - 1) // (1024 * hp.slice_words)
     perms = draw_perms(17, 1500, 150).astype(np.uint16)
+    assert np.array_equal(eng.curves_host(perms), _oracle_curves(coo, perms))
+
+
+@pytest.mark.parametrize("slice_words", [1, 2, 4])
+def test_bitmap_slices_of_1_2_4_words(engine_mod, slice_words):
+    """The probe walk with 1, 2 and 4 words per lane: several superblocks, the last one ragged."""
+    from pangenomix_b200.plan import build_host_plan
+    coo = _mixed_matrix(600, seed=21, per_class=600)
+    hp = build_host_plan(coo, long_threshold=6, slice_words=slice_words)
+    assert hp.n_long > 4096 and hp.n_superblocks >= 2
+    eng = engine_mod.PanCoreEngine(coo, host_plan=hp)
+    perms = draw_perms(23, 600, 70).astype(np.uint16)
     assert np.array_equal(eng.curves_host(perms), _oracle_curves(coo, perms))
 
 

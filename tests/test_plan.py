@@ -61,7 +61,7 @@ def test_plan_list_and_bitmap_rows(threshold, perms_per_cta):
         assert hp.n_long == 0
     else:
         assert hp.n_long > 0 and np.all(hp.row_len < threshold)
-        assert hp.bits.shape[0] == hp.n_superblocks * n * 32
+        assert hp.bits.shape[0] == hp.n_superblocks * n * 32 * hp.slice_words
     if threshold == 2:
         assert hp.n_rows == 0
     wavefronts = check_layout(hp)
@@ -71,6 +71,23 @@ def test_plan_list_and_bitmap_rows(threshold, perms_per_cta):
     import oracle
     pan, core = oracle.pan_core_curves_minrank(scipy.sparse.coo_matrix(x), perms)
     assert np.array_equal(curves_from_plan(hp, perms), np.hstack([pan, core]).astype(np.int64))
+
+
+@pytest.mark.parametrize("slice_words", [1, 2, 4])
+def test_plan_bitmap_slices_of_1_2_4_words(slice_words):
+    """Superblocks of 1,024 / 2,048 / 4,096 rows: several of them, the last one ragged."""
+    x = _mixed_matrix(300, seed=11, per_class=700)
+    coo = scipy.sparse.coo_matrix(x)
+    hp = build_host_plan(coo, long_threshold=4, slice_words=slice_words)
+    assert hp.slice_words == slice_words and hp.n_long > 4096
+    assert hp.n_superblocks == -(-hp.n_long // (1024 * slice_words))
+    assert hp.bits.shape[0] == hp.n_superblocks * 300 * 32 * slice_words
+    perms = draw_perms(7, 300, 2)
+    import oracle
+    pan, core = oracle.pan_core_curves_minrank(coo, perms)
+    assert np.array_equal(curves_from_plan(hp, perms), np.hstack([pan, core]).astype(np.int64))
+    with pytest.raises(ValueError):
+        build_host_plan(coo, slice_words=3)
 
 
 def test_plan_bank_order_beats_sorted_order():
