@@ -475,6 +475,7 @@ int launch_list(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm,
                 const DeviceLimits &lim, cudaStream_t stream)
 {
     int threads = g_tuning.threads;
+    if (threads <= 0 && getenv("PGX_LIST_THREADS")) threads = atoi(getenv("PGX_LIST_THREADS"));
     const size_t table_bytes = ((static_cast<size_t>(plan.n_genomes + SENTINELS) * B + 7) & ~size_t(7)) * sizeof(uint16_t);
     if (threads <= 0) threads = table_bytes > 100 * 1024 ? 1024 : (table_bytes > 40 * 1024 ? 512 : 256);
     threads = max(32, min(1024, (threads / 32) * 32));

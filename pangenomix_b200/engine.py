@@ -35,11 +35,6 @@ def _require_cuda(device=None):
     return device
 
 
-def _u16_view(t):
-    """torch has few uint16 ops; device buffers of uint16 data are carried as int16."""
-    return t
-
-
 def pinned_empty(shape, dtype):
     """numpy array backed by page-locked memory (returns (array, owner tensor))."""
     torch = _torch()

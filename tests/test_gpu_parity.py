@@ -142,6 +142,34 @@ def test_wide_tables_fall_back_to_smaller_batches(engine_mod, n):
     assert np.array_equal(lists_only.curves_host(perms[:2]), _oracle_curves(coo, perms[:2]))
 
 
+def test_random_tables_every_layout_choice(engine_mod):
+    """40 random tables (shape, density profile, threshold, batch size, slice width all drawn at random)
+    through the CUDA path, against the oracle, bit for bit."""
+    from pangenomix_b200 import _native
+    from pangenomix_b200.plan import build_host_plan
+    rng = np.random.RandomState(20260101)
+    try:
+        for case in range(40):
+            n = int(rng.choice([1, 2, 3, 7, 31, 32, 33, 64, 100, 257, 400]))
+            g = int(rng.choice([0, 1, 5, 40, 300, 1500]))
+            style = rng.choice(["mixed", "sparse", "dense", "half"])
+            dens = {"mixed": rng.choice([0.0, 0.03, 0.1, 0.3, 0.5, 0.8, 0.97, 1.0], size=g),
+                    "sparse": rng.uniform(0.0, 0.1, size=g), "dense": rng.uniform(0.9, 1.0, size=g),
+                    "half": np.full(g, 0.5)}[style]
+            x = (rng.random_sample((g, n)) < dens[:, None]).astype(np.int64)
+            coo = scipy.sparse.coo_matrix(x)
+            hp = build_host_plan(coo, long_threshold=int(rng.choice([0, 2, 4, 9, 30])),
+                                 perms_per_cta=int(rng.choice([1, 2, 4, 8])), slice_words=int(rng.choice([1, 2, 4])))
+            eng = engine_mod.PanCoreEngine(coo, host_plan=hp)
+            _native.set_tuning(0, int(rng.choice([0, 1, 5])), int(rng.choice([0, 64, 256, 1024])))
+            n_perm = int(rng.choice([1, 7, 8, 9, 129]))
+            perms = np.stack([rng.permutation(n) for _ in range(n_perm)]).astype(np.uint16)
+            got = eng.curves_host(perms)
+            assert np.array_equal(got, _oracle_curves(coo, perms)), (case, n, g, style)
+    finally:
+        _native.set_tuning(0, 0, 0)
+
+
 def test_degenerate_shapes(engine_mod):
     import torch
     # no folded rows at all: everything is a closed form

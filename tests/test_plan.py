@@ -94,3 +94,36 @@ def test_plan_bank_order_beats_sorted_order():
     x = _mixed_matrix(4000, seed=9, per_class=64)
     hp = build_host_plan(scipy.sparse.coo_matrix(x), long_threshold=0, perms_per_cta=8)
     assert check_layout(hp) < 1.6
+
+
+def test_plan_random_tables_property():
+    """Property test (hypothesis): for random binary tables, thresholds, batch sizes and slice widths the
+    device layout, walked like the kernels walk it, gives the curves of the min-rank oracle; and the
+    curves obey the invariants SURVEY.md section 4 lists."""
+    import oracle
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=60, deadline=None)
+    @given(n=st.integers(1, 70), g=st.integers(0, 160), seed=st.integers(0, 10 ** 6),
+           threshold=st.sampled_from([0, 2, 3, 5, 9, 17, 40]), perms_per_cta=st.sampled_from([1, 2, 4, 8]),
+           slice_words=st.sampled_from([1, 2, 4]), style=st.sampled_from(["mixed", "sparse", "dense", "half"]))
+    def check(n, g, seed, threshold, perms_per_cta, slice_words, style):
+        rng = np.random.RandomState(seed)
+        dens = {"mixed": rng.choice([0.0, 0.03, 0.1, 0.3, 0.5, 0.8, 0.97, 1.0], size=g),
+                "sparse": rng.uniform(0.0, 0.1, size=g), "dense": rng.uniform(0.9, 1.0, size=g),
+                "half": np.full(g, 0.5)}[style]
+        x = (rng.random_sample((g, n)) < dens[:, None]).astype(np.int64)
+        coo = scipy.sparse.coo_matrix(x)
+        hp = build_host_plan(coo, long_threshold=threshold, perms_per_cta=perms_per_cta, slice_words=slice_words)
+        assert hp.n_rows + hp.n_long + hp.n_empty + hp.n_full + hp.w_present.sum() + hp.w_absent.sum() == g
+        check_layout(hp)
+        perms = np.stack([rng.permutation(n) for _ in range(3)])
+        got = curves_from_plan(hp, perms)
+        pan, core = oracle.pan_core_curves_minrank(coo, perms)
+        assert np.array_equal(got, np.hstack([pan, core]).astype(np.int64))
+        counts = x.sum(axis=1)
+        assert np.all(np.diff(got[:, :n], axis=1) >= 0) and np.all(np.diff(got[:, n:], axis=1) <= 0)
+        assert np.array_equal(got[:, 0], got[:, n])
+        assert np.all(got[:, n - 1] == np.count_nonzero(counts)) and np.all(got[:, 2 * n - 1] == np.count_nonzero(counts == n))
+
+    check()
