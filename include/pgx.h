@@ -162,6 +162,28 @@ size_t pgx_heaps_scratch_bytes(int64_t n_points);
 int pgx_heaps_fit(const void *d_curves, int32_t is_f64, int64_t n_curves, int64_t n_points, int64_t stride,
                   double *d_fit, int32_t *d_info, void *d_scratch, void *stream);
 
+/* Host-side helper of the planner (no GPU work): orders the entries of the list rows so that the lanes
+ * of a shared-memory wavefront of the list kernel hit distinct banks (pangenomix_b200/plan.py,
+ * _bank_ordered_chunks; the layout is the one struct pgx_plan documents).
+ *   flat / ptr        : sorted folded lists of the n_rows list rows, concatenated (int32) / offsets (int64)
+ *   block_*           : per sub-block of 32 rows: first chunk, chunks per row, first row, rows (int64 [n_blocks])
+ *   modulus           : lanes per 128-byte wavefront: 8, 16 or 32 (= 64 / perms_per_cta, capped)
+ *   colour_max_chunks : rows of more chunks use the cheap positional order instead of the edge colouring
+ *   chunks            : out, uint16 [sum(block_nch) * 32 * 8]
+ *   n_threads         : host threads (0 = choose) */
+int pgx_plan_bank_order(const int32_t *flat, const int64_t *ptr, int64_t n_rows,
+                        const int64_t *block_first, const int64_t *block_nch,
+                        const int64_t *block_first_row, const int64_t *block_rows, int64_t n_blocks,
+                        int32_t n_genomes, int32_t modulus, int32_t colour_max_chunks,
+                        uint16_t *chunks, int32_t n_threads);
+
+/* Host-side helper of the planner: the bit-sliced bitmap d_bits of struct pgx_plan for the long rows
+ * ``long_gene`` (gene ids, in superblock order) of a gene-major CSR (indptr int64, indices int32).
+ * ``bits`` (uint32 [n_superblocks * n_genomes * 32 * slice_words]) must be zero-initialised. */
+int pgx_plan_build_bitmap(const int64_t *indptr, const int32_t *indices, const int64_t *long_gene,
+                          int64_t n_long, int32_t n_genomes, int32_t slice_words, uint32_t *bits,
+                          int32_t n_threads);
+
 /* numpy legacy RandomState stream (host): ``count`` consecutive
  * ``a = np.arange(n); np.random.shuffle(a)`` results as uint16 rows, continuing from the
  * MT19937 state in ``mt_key`` (624 words) / ``mt_pos`` exactly as

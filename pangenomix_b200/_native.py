@@ -18,6 +18,7 @@ EXPORTS = (
     "pgx_launch_count", "pgx_bernoulli_scratch_bytes", "pgx_bernoulli_ll_grad",
     "pgx_legacy_shuffles", "pgx_profile_enable", "pgx_profile_read",
     "pgx_heaps_scratch_bytes", "pgx_heaps_fit", "pgx_estimate_pan_core",
+    "pgx_plan_bank_order", "pgx_plan_build_bitmap",
 )
 
 
@@ -84,6 +85,10 @@ def load():
     lib.pgx_bernoulli_scratch_bytes.argtypes = [i64, i64]
     lib.pgx_bernoulli_ll_grad.restype = ctypes.c_int
     lib.pgx_bernoulli_ll_grad.argtypes = [vp, i64, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.pgx_plan_build_bitmap.restype = ctypes.c_int
+    lib.pgx_plan_build_bitmap.argtypes = [vp, vp, vp, i64, i32, i32, vp, i32]
+    lib.pgx_plan_bank_order.restype = ctypes.c_int
+    lib.pgx_plan_bank_order.argtypes = [vp, vp, i64, vp, vp, vp, vp, i64, i32, i32, i32, vp, i32]
     lib.pgx_estimate_pan_core.restype = ctypes.c_int
     lib.pgx_estimate_pan_core.argtypes = [plan_p, vp, ctypes.POINTER(i32), i64, vp, i64]
     lib.pgx_heaps_scratch_bytes.restype = ctypes.c_size_t

@@ -51,8 +51,10 @@ SMEM_TABLE_BUDGET = 220 * 1024
 def default_long_threshold(n_genomes):
     """Folded length from which a gene is cheaper to serve from the bit-sliced bitmap (a walk of
     ~N/m coalesced lines shared by 1,024 genes) than from its list (m shared-memory gathers):
-    the measured break-even on B200 is close to 1.3 sqrt(N) (profiles/)."""
-    return max(8, int(round(1.28 * np.sqrt(n_genomes))))
+    the measured break-even on B200 is close to 1.3 sqrt(N) while 8 permutations share every gather
+    (N <= 14k; flat between 128 and 160 at N = 10,000) and about 200 at N = 50,000, where only 2 do."""
+    batch = perms_per_cta_for(n_genomes)           # fewer permutations share a gather on wide tables
+    return max(8, int(round(1.28 * np.sqrt(n_genomes) * (batch / 8.0) ** 0.25)))
 
 _COMPLEMENT_BLOCK_CELLS = 1 << 26
 
@@ -287,7 +289,7 @@ def _positional_groups(cnt, n_steps):
     return res_at, pad_res
 
 
-def _bank_ordered_chunks(flat, ptr, block_first, block_nch, block_first_row, block_rows, n, modulus):
+def _bank_ordered_chunks_numpy(flat, ptr, block_first, block_nch, block_first_row, block_rows, n, modulus):
     """Lays the list rows out for the lane-per-row kernel.
 
     Lane l of a sub-block reads chunk ``first + it * 32 + l`` at iteration ``it`` and gathers the
@@ -347,6 +349,51 @@ def _bank_ordered_chunks(flat, ptr, block_first, block_nch, block_first_row, blo
     return chunks
 
 
+def _build_bitmap(indptr, indices, m, long_gene, n, slice_words):
+    """Genome-major bit-sliced bitmap of the long rows (include/pgx.h, d_bits).  Host helper
+    pgx_plan_build_bitmap; PGX_PLAN_NUMPY=1 selects the numpy specification (dense block + packbits)."""
+    import os
+    sb_rows = SLICE_ROWS * slice_words
+    n_super = (long_gene.size + sb_rows - 1) // sb_rows
+    if os.environ.get("PGX_PLAN_NUMPY") == "1":
+        bits = np.zeros((n_super, n, sb_rows // 32), dtype=np.uint32)
+        for sb in range(n_super):
+            rows = long_gene[sb * sb_rows:(sb + 1) * sb_rows]
+            lens = m[rows]
+            src = np.repeat(indptr[rows], lens) + _segment_positions(lens)
+            dense = np.zeros((n, sb_rows), dtype=bool)                       # [genome][row in superblock]
+            dense[indices[src], np.repeat(np.arange(rows.size), lens)] = True
+            bits[sb] = np.packbits(dense, axis=1, bitorder="little").view(np.uint32)
+        return bits.reshape(-1)
+    from . import _native
+    bits = np.zeros(n_super * n * (sb_rows // 32), dtype=np.uint32)
+    ip = np.ascontiguousarray(indptr, dtype=np.int64)
+    ix = np.ascontiguousarray(indices, dtype=np.int32)
+    lg = np.ascontiguousarray(long_gene, dtype=np.int64)
+    _native.check(_native.load().pgx_plan_build_bitmap(
+        ip.ctypes.data, ix.ctypes.data, lg.ctypes.data, lg.shape[0], int(n), int(slice_words), bits.ctypes.data, 0))
+    return bits
+
+
+def _bank_ordered_chunks(flat, ptr, block_first, block_nch, block_first_row, block_rows, n, modulus):
+    """The bank ordering through libpgx's host helper pgx_plan_bank_order (csrc/pgx_plan.cpp: the same
+    algorithm as ``_bank_ordered_chunks_numpy`` with identical output, as plain threaded loops);
+    PGX_PLAN_NUMPY=1 selects the numpy specification instead."""
+    import os
+    if os.environ.get("PGX_PLAN_NUMPY") == "1":
+        return _bank_ordered_chunks_numpy(flat, ptr, block_first, block_nch, block_first_row, block_rows, n, modulus)
+    from . import _native
+    lib = _native.load()
+    flat32 = np.ascontiguousarray(flat, dtype=np.int32)
+    arrays = [np.ascontiguousarray(a, dtype=np.int64) for a in (ptr, block_first, block_nch, block_first_row, block_rows)]
+    chunks = np.empty(int((arrays[2] * (32 * CHUNK)).sum()), dtype=np.uint16)
+    _native.check(lib.pgx_plan_bank_order(
+        flat32.ctypes.data, arrays[0].ctypes.data, arrays[0].shape[0] - 1, arrays[1].ctypes.data,
+        arrays[2].ctypes.data, arrays[3].ctypes.data, arrays[4].ctypes.data, arrays[2].shape[0],
+        int(n), int(modulus), COLOUR_MAX_CHUNKS, chunks.ctypes.data, 0))
+    return chunks
+
+
 def build_host_plan(data, long_threshold=None, perms_per_cta=None, slice_words=None) -> HostPlan:
     csr = gene_major_csr(data)
     n_genes, n = csr.shape
@@ -403,15 +450,7 @@ def build_host_plan(data, long_threshold=None, perms_per_cta=None, slice_words=N
         m_long = m[long_gene]
         order = np.argsort(np.minimum(m_long, n - m_long), kind="stable")   # longest walks first
         long_gene = long_gene[order]
-        bits = np.zeros((n_super, n, sb_rows // 32), dtype=np.uint32)
-        for sb in range(n_super):
-            rows = long_gene[sb * sb_rows:(sb + 1) * sb_rows]
-            lens = m[rows]
-            src = np.repeat(indptr[rows], lens) + _segment_positions(lens)
-            dense = np.zeros((n, sb_rows), dtype=bool)                       # [genome][row in superblock]
-            dense[indices[src], np.repeat(np.arange(rows.size), lens)] = True
-            bits[sb] = np.packbits(dense, axis=1, bitorder="little").view(np.uint32)
-        bits = bits.reshape(-1)
+        bits = _build_bitmap(indptr, indices, m, long_gene, n, slice_words)
     else:
         bits = np.zeros(0, dtype=np.uint32)
 

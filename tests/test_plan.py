@@ -90,6 +90,27 @@ def test_plan_bitmap_slices_of_1_2_4_words(slice_words):
         build_host_plan(coo, slice_words=3)
 
 
+@pytest.mark.parametrize("perms_per_cta", [8, 4, 2])
+def test_plan_native_bank_order_equals_numpy_specification(monkeypatch, perms_per_cta):
+    """pgx_plan_bank_order (C++, threaded) must reproduce plan._bank_ordered_chunks_numpy bit for bit:
+    the colouring for short rows, the positional order for long ones, pads, ragged sub-blocks."""
+    x = _mixed_matrix(1300, seed=31, per_class=90)
+    coo = scipy.sparse.coo_matrix(x)
+    native = build_host_plan(coo, long_threshold=0, perms_per_cta=perms_per_cta)
+    monkeypatch.setenv("PGX_PLAN_NUMPY", "1")
+    spec = build_host_plan(coo, long_threshold=0, perms_per_cta=perms_per_cta)
+    assert (native.tasks[:, 1] & 0xFFFF).max() > 32 > (native.tasks[:, 1] & 0xFFFF).min()      # both orderings in play
+    assert np.array_equal(native.chunks, spec.chunks)
+    assert np.array_equal(native.tasks, spec.tasks)
+    monkeypatch.delenv("PGX_PLAN_NUMPY")
+    for w in (1, 2, 4):
+        a = build_host_plan(coo, long_threshold=5, slice_words=w)
+        monkeypatch.setenv("PGX_PLAN_NUMPY", "1")
+        b = build_host_plan(coo, long_threshold=5, slice_words=w)
+        monkeypatch.delenv("PGX_PLAN_NUMPY")
+        assert a.n_long > 0 and np.array_equal(a.bits, b.bits) and np.array_equal(a.chunks, b.chunks)
+
+
 def test_plan_bank_order_beats_sorted_order():
     x = _mixed_matrix(4000, seed=9, per_class=64)
     hp = build_host_plan(scipy.sparse.coo_matrix(x), long_threshold=0, perms_per_cta=8)
