@@ -573,6 +573,39 @@ def run_bernoulli(args):
     got_ll, got_grad = grid.ll_grad(pts[0])
     np.testing.assert_allclose(got_ll, ref_ll, rtol=1e-9)
     np.testing.assert_allclose(got_grad, ref_grad, rtol=1e-9, atol=1e-9 * np.abs(ref_grad).max())
+    # the reference-facing call itself: the whole L-BFGS-B fit (scipy on the host drives the kernels),
+    # and the same fit with the reference's numpy likelihood on one core (bounded: 4,000 genes)
+    import contextlib
+    import io
+    import warnings
+    import pandas as pd
+    import scipy.optimize
+    from pangenomix_b200 import pangenome_analysis as pa
+    index, columns = synth.labels_for(g, n)
+    df_dense = pd.DataFrame(x, index=index, columns=columns)
+    with warnings.catch_warnings(), contextlib.redirect_stdout(io.StringIO()):
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter()
+        df_opt, res = pa.compute_bernoulli_grid_core_genome(df_dense)
+        fit_s = time.perf_counter() - t0
+    fit = {"call": "compute_bernoulli_grid_core_genome(df %d x %d)" % (g, n), "seconds": fit_s,
+           "iterations": int(res.nit), "evaluations": int(res.nfev), "final_loglikelihood": float(-res.fun),
+           "message": str(res.message)}
+    g_ref = min(g, 4000)
+    x_ref = x[:g_ref]
+    p0 = np.clip(np.concatenate((x_ref.sum(axis=1) / float(n), 0.9999 * np.ones(n))), 0.8, 0.99999999)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        t0 = time.perf_counter()
+        ref = scipy.optimize.minimize(lambda v: -oracle.bernoulli_ll(x_ref, v[:g_ref], v[g_ref:]), p0, method="L-BFGS-B",
+                                      jac=lambda v: -oracle.bernoulli_grad(x_ref, v[:g_ref], v[g_ref:]),
+                                      bounds=[(0.8, 0.99999999)] * (g_ref + n))
+        ref_s = time.perf_counter() - t0
+    fit["reference_numpy_fit_seconds_%d_genes" % g_ref] = ref_s
+    fit["reference_numpy_fit_iterations"] = int(ref.nit)
+    if g_ref == g:
+        fit["optimum_rel_diff_vs_reference"] = float(abs(res.fun - ref.fun) / abs(ref.fun))
+
     absent = int(x.size - x.sum())
     value = steps / (ms / 1e3)
     peak, peak_src = measured_peak()
@@ -599,6 +632,7 @@ def run_bernoulli(args):
                 "d2h_bytes_per_step": 8 * (g + n + 1), "ms_per_step": e2e_s / steps * 1e3,
                 "path": "BernoulliGrid.ll_grad: pinned P,Q up, 2 kernels, LL + gradient down"},
         "gpu_launches": int(launches), "clocks": clocks,
+        "fit": fit,
         "parity": {"ll_rel_err": abs(got_ll - ref_ll) / abs(ref_ll),
                    "grad_max_rel_err": float(np.max(np.abs(got_grad - ref_grad)) / np.abs(ref_grad).max())},
     }
