@@ -854,6 +854,7 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
         }
     });
     int rc = PGX_OK;
+    const int copy_threads = std::max(1, std::min(4, static_cast<int>(std::thread::hardware_concurrency()) / 2));
     for (long long k = 0; k < n_blocks; ++k) {
         {
             std::unique_lock<std::mutex> lk(mu);
@@ -869,7 +870,20 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
             cv.notify_all();
             break;
         }
-        memcpy(h_curves + p0 * 2 * n, s.h_out, sizeof(double) * cnt * 2 * n);
+        {
+            // staging -> result with a few threads: one core fills fresh pages at only ~8 GB/s
+            const size_t bytes = sizeof(double) * cnt * 2 * n;
+            char *dst = reinterpret_cast<char *>(h_curves + p0 * 2 * n);
+            const char *src = reinterpret_cast<const char *>(s.h_out);
+            const int parts = bytes >= (8u << 20) ? copy_threads : 1;
+            std::vector<std::thread> movers;
+            for (int t = 1; t < parts; ++t) {
+                const size_t lo = bytes / parts * t, hi = t + 1 == parts ? bytes : bytes / parts * (t + 1);
+                movers.emplace_back([=]() { memcpy(dst + lo, src + lo, hi - lo); });
+            }
+            memcpy(dst, src, parts > 1 ? bytes / parts : bytes);
+            for (auto &m : movers) m.join();
+        }
         {
             std::lock_guard<std::mutex> lk(mu);
             retired = k + 1;
