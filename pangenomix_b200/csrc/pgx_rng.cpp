@@ -7,7 +7,7 @@
 //
 // The stream is serial, but only two of its three stages are: (1) generating raw MT19937
 // words and (2) deciding which words are accepted (that decides where the next shuffle
-// starts).  Both are vectorised here (AVX2 when the CPU has it).  Stage (3), applying the
+// starts).  Both are vectorised here (AVX-512 or AVX2 when the CPU has it).  Stage (3), applying the
 // accepted swap targets to the identity permutation, is independent per shuffle and runs
 // on worker threads, two shuffles interleaved per thread for instruction-level parallelism.
 #include <stdint.h>
@@ -45,6 +45,7 @@ struct Mt19937 {
     alignas(64) uint32_t out[624 + 8];
     int pos;
     bool avx2;
+    bool avx512 = false;
 
     static inline uint32_t twist(uint32_t a, uint32_t b, uint32_t far)
     {
@@ -116,9 +117,51 @@ struct Mt19937 {
     }
 #endif
 
+#if PGX_X86
+    __attribute__((target("avx512f"))) static inline __m512i twist16(__m512i a, __m512i b, __m512i far)
+    {
+        const __m512i y = _mm512_or_si512(_mm512_and_si512(a, _mm512_set1_epi32(static_cast<int>(MT_UPPER))),
+                                          _mm512_and_si512(b, _mm512_set1_epi32(static_cast<int>(MT_LOWER))));
+        const __m512i odd = _mm512_sub_epi32(_mm512_setzero_si512(), _mm512_and_si512(y, _mm512_set1_epi32(1)));
+        return _mm512_xor_si512(_mm512_xor_si512(far, _mm512_srli_epi32(y, 1)),
+                                _mm512_and_si512(odd, _mm512_set1_epi32(static_cast<int>(MT_MAGIC))));
+    }
+
+    __attribute__((target("avx512f"))) void refill_avx512()
+    {
+        int k = 0;
+        for (; k + 16 <= 227; k += 16) {
+            const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
+            const __m512i f = _mm512_loadu_si512(key + k + 397);
+            _mm512_storeu_si512(key + k, twist16(a, b, f));
+        }
+        for (; k < 227; ++k) key[k] = twist(key[k], key[k + 1], key[k + 397]);
+        for (; k + 16 <= 623; k += 16) {
+            const __m512i a = _mm512_loadu_si512(key + k), b = _mm512_loadu_si512(key + k + 1);
+            const __m512i f = _mm512_loadu_si512(key + k - 227);
+            _mm512_storeu_si512(key + k, twist16(a, b, f));
+        }
+        for (; k < 623; ++k) key[k] = twist(key[k], key[k + 1], key[k - 227]);
+        key[623] = twist(key[623], key[0], key[396]);
+        for (k = 0; k < 624; k += 16) {
+            __m512i y = _mm512_load_si512(key + k);
+            y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 11));
+            y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 7), _mm512_set1_epi32(static_cast<int>(0x9d2c5680u))));
+            y = _mm512_xor_si512(y, _mm512_and_si512(_mm512_slli_epi32(y, 15), _mm512_set1_epi32(static_cast<int>(0xefc60000u))));
+            y = _mm512_xor_si512(y, _mm512_srli_epi32(y, 18));
+            _mm512_store_si512(out + k, y);
+        }
+    }
+#endif
+
     void refill()
     {
 #if PGX_X86
+        if (avx512) {
+            refill_avx512();
+            pos = 0;
+            return;
+        }
         if (avx2) {
             refill_avx2();
             pos = 0;
@@ -200,6 +243,36 @@ void accept_avx2_span(Mt19937 &mt, uint32_t &i_io, uint32_t lo, uint32_t mask, u
 }
 #endif
 
+#if PGX_X86
+__attribute__((target("avx512f,popcnt")))
+void accept_avx512_span(Mt19937 &mt, uint32_t &i_io, uint32_t lo, uint32_t mask, uint32_t *&w_io)
+{
+    uint32_t i = i_io;
+    uint32_t *w = w_io;
+    int pos = mt.pos;
+    const __m512i maskv = _mm512_set1_epi32(static_cast<int>(mask));
+    // 16 draws per vector: lane l is tested against i - (accepts among lanes < l), in [i - 15, i]
+    while (i >= lo + 16) {
+        if (pos + 16 > 624) {
+            if (pos >= 624) { mt.refill(); pos = 0; continue; }
+            break;                                   // block tail: the scalar loop finishes it
+        }
+        const __m512i v = _mm512_and_si512(_mm512_loadu_si512(mt.out + pos), maskv);
+        const __mmask16 sure = _mm512_cmple_epu32_mask(v, _mm512_set1_epi32(static_cast<int>(i - 15)));
+        const __mmask16 over = _mm512_cmpgt_epu32_mask(v, _mm512_set1_epi32(static_cast<int>(i)));
+        if (static_cast<unsigned>(sure | over) != 0xffffu) break;    // an ambiguous lane: resolve this vector one by one
+        _mm512_storeu_si512(w, _mm512_maskz_compress_epi32(sure, v));
+        const uint32_t got = static_cast<uint32_t>(_mm_popcnt_u32(static_cast<unsigned>(sure)));
+        w += got;
+        i -= got;
+        pos += 16;
+    }
+    mt.pos = pos;
+    i_io = i;
+    w_io = w;
+}
+#endif
+
 void accept_one(Mt19937 &mt, uint32_t n, uint32_t *js)
 {
     if (n < 2) return;
@@ -212,12 +285,14 @@ void accept_one(Mt19937 &mt, uint32_t n, uint32_t *js)
 #if PGX_X86
         if (mt.avx2 && mask < 0x80000000u) {
             // alternate: vector spans while far from lo and unambiguous, scalar for what is left
+            const uint32_t stretch = mt.avx512 ? 16 : 8;
             while (i >= lo) {
-                accept_avx2_span(mt, i, lo, mask, w);
+                if (mt.avx512) accept_avx512_span(mt, i, lo, mask, w);
+                else accept_avx2_span(mt, i, lo, mask, w);
                 if (i < lo) break;
-                // one scalar draw-by-draw stretch of at most 8 draws, then try vectors again
+                // one scalar draw-by-draw stretch of at most a vector's worth of draws, then try vectors again
                 uint32_t done = 0;
-                while (i >= lo && done < 8) {
+                while (i >= lo && done < stretch) {
                     if (mt.pos >= 624) mt.refill();
                     const uint32_t v = mt.out[mt.pos++] & mask;
                     const uint32_t ok = v <= i;
@@ -297,13 +372,15 @@ extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n,
     mt.pos = *mt_pos;
 #if PGX_X86
     mt.avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt") && !getenv("PGX_RNG_SCALAR");
+    mt.avx512 = mt.avx2 && __builtin_cpu_supports("avx512f") && !getenv("PGX_RNG_NO_AVX512");
 #else
     mt.avx2 = false;
+    mt.avx512 = false;
 #endif
     mt.temper_scalar();
 
     const uint32_t un = static_cast<uint32_t>(n);
-    const size_t stride = static_cast<size_t>(n) + 8;          // js row, with room for vector overrun
+    const size_t stride = static_cast<size_t>(n) + 16;         // js row, with room for vector overrun
     const int batch = static_cast<int>(std::max<int64_t>(2, std::min<int64_t>(64, (1 << 17) / std::max<int64_t>(n, 1))));
     int workers = (n >= 64 && count >= 4 * batch) ? worker_threads_wanted() : 0;
 

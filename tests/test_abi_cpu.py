@@ -60,11 +60,13 @@ def test_legacy_shuffles_are_numpys(n):
 
 
 @pytest.mark.parametrize("n,count", [(7, 5000), (64, 3000), (400, 2500), (10000, 120), (65503, 24)])
-@pytest.mark.parametrize("mode", ["default", "scalar", "one_thread", "seven_threads"])
+@pytest.mark.parametrize("mode", ["default", "avx2", "scalar", "one_thread", "seven_threads"])
 def test_legacy_shuffles_vector_and_threaded_paths(monkeypatch, n, count, mode):
     """Long streams exercise the AVX2 acceptance spans, every mask boundary, MT19937 block
     boundaries inside a vector and the producer / worker-thread pipeline; all must equal numpy."""
-    if mode == "scalar":
+    if mode == "avx2":
+        monkeypatch.setenv("PGX_RNG_NO_AVX512", "1")
+    elif mode == "scalar":
         monkeypatch.setenv("PGX_RNG_SCALAR", "1")
     elif mode == "one_thread":
         monkeypatch.setenv("PGX_RNG_THREADS", "0")
