@@ -154,6 +154,7 @@ class CurveGather:
                 self._stream = torch.cuda.Stream(self.device)
                 self._ready = [torch.cuda.Event() for _ in range(self.n_buffers)]
                 self._done = [None] * self.n_buffers
+                self._own = [None] * self.n_buffers
                 self.mode = "peer-push"
             except Exception as exc:                                   # noqa: BLE001 - any failure means "no peer path"
                 self._peer = None
@@ -175,6 +176,10 @@ class CurveGather:
         """Ships ``block`` (int32 [rows, width], produced on the current stream) as buffer ``b``."""
         torch = self.torch
         if self._peer is not None:
+            if self.rank == self.dst:
+                # the destination's own block does not travel: gathered() reads it where it is
+                self._own[b] = block
+                return
             self._ready[b].record(torch.cuda.current_stream(self.device))
             with torch.cuda.stream(self._stream):
                 self._stream.wait_event(self._ready[b])
@@ -192,10 +197,13 @@ class CurveGather:
             self.before_overwrite(b)
 
     def gathered(self, b):
-        """On ``dst``: the [world, rows, width] blocks of buffer ``b`` (valid after every rank drained
-        and the ranks passed a barrier)."""
+        """On ``dst``: the list of the ``world`` [rows, width] blocks of buffer ``b`` (valid after every
+        rank drained and the ranks passed a barrier)."""
         if self.rank != self.dst:
             return None
         if self._peer is not None:
-            return self._peer[b]
-        return self.torch.stack(self._lists[b])
+            blocks = [self._peer[b, r] for r in range(self.world)]
+            if self._own[b] is not None:
+                blocks[self.dst] = self._own[b]
+            return blocks
+        return list(self._lists[b])

@@ -99,10 +99,10 @@ def _gather_worker(rank, world, port, result_dir):
     dist.barrier()
     if rank == 0:
         for b, step in last.items():
-            got = gather.gathered(b).numpy()
-            assert got.shape == (world, rows, width)
+            got = gather.gathered(b)
+            assert len(got) == world and tuple(got[0].shape) == (rows, width)
             for r in range(world):
-                assert np.all(got[r] == 1000 * step + r)
+                assert np.all(got[r].numpy() == 1000 * step + r)
         np.save(os.path.join(result_dir, "ok.npy"), np.ones(1))
     else:
         assert gather.gathered(0) is None
