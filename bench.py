@@ -52,8 +52,9 @@ def parse_args():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c4", "c3"],
-                    help="c4/c2/c1: pan/core rarefaction (the headline metric); c3: Bernoulli-grid LL+gradient")
+    ap.add_argument("--workload", default="c4", choices=["c1", "c2", "c4", "c5", "c3"],
+                    help="c4/c2/c1/c5: pan/core rarefaction (c4 is the headline metric; c5 = 50,000 genomes x 2,000,000 "
+                         "alleles needs minutes of host time to generate and plan); c3: Bernoulli-grid LL+gradient")
     ap.add_argument("--genes", type=int, default=40000, help="c3: genes of the Bernoulli grid (400 genomes)")
     ap.add_argument("--perms", type=int, default=0, help="permutations per GPU per step (0 = the config's)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
