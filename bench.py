@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """bench.py -- pan/core permutations per second on B200 (BASELINE.json's metric).
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c1] [--perms P]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload c4|c2|c1|c5|c3] [--perms P]
     python bench.py --impl reference ...          # the CPU arm (oracle C port, all host threads)
     torchrun --nproc-per-node N ... bench.py --gpus N ...   # one rank per GPU
 
@@ -12,15 +12,22 @@ configuration the north_star's roofline and scaling targets are quoted on.
 
   value : permutations/s, table and permutations resident in HBM, CUDA-event timed,
           max over ranks (weak scaling: every rank rarefies its own P permutations of the
-          replicated table; for N > 1 the curves are gathered to rank 0 over NCCL inside
-          the timed region).
+          replicated table; for N > 1 the int32 curves of every step are gathered on rank 0
+          inside the timed region -- pushed into rank 0's symmetric-memory buffer over NVLink,
+          asynchronously, overlapped with the next step; NCCL gather as fallback).
   e2e   : the same through the host-buffer C-ABI call (pinned host permutations in,
           host curves out; copies inside the timed region).
-  roofline : row kernel only, algorithmic bytes of SURVEY.md section 8d
-          (4 nnz + 4 (G + 1) per permutation) over its CUDA-event duration, against the
-          measured HBM copy bandwidth of MEASURED_PEAKS.json.
+  roofline : the slower of the two row kernels against ITS share of the algorithmic bytes of
+          SURVEY.md section 8d (4 nnz + 4 (G + 1) per permutation for the whole table), over its
+          CUDA-event duration (a separate pass: the timed region runs the two kernels side by
+          side), against the measured HBM copy bandwidth of MEASURED_PEAKS.json; traffic = DRAM
+          bytes of that kernel from the committed ncu capture (profiles/roofline_traffic.json).
   cpu_baseline : the oracle's C port of the reference algorithm on a bounded sample.
-One JSON line on stdout (rank 0).
+  api   : the reference-facing Python call itself, estimate_pan_core_size(df, 2000): host RNG
+          stream + H2D + kernels + D2H + float64 DataFrame.
+  heaps : pgx_heaps_fit on the curves of one step next to scipy curve_fit.
+--workload c3 prints the same kind of line for the Bernoulli grid (LL + gradient evaluations/s,
+whole-fit time).  One JSON line on stdout (rank 0); everything else goes to stderr.
 """
 import argparse
 import json
