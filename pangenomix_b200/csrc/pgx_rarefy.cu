@@ -143,8 +143,11 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
     // Persistent CTAs: item = (batch of B permutations, share ``split`` of the tasks).  The whole
     // grid is resident at once, so CTAs of the probe kernel can fill the rest of every SM.
     for (long long item = blockIdx.x; item < n_items; item += gridDim.x) {
-    const long long p0 = (item / splits) * B;
-    const int split = static_cast<int>(item % splits);
+    // split-major: CTAs that run at the same time stream the SAME share of the chunks for different
+    // batches, so a table whose chunks exceed L2 (C5: 128 MB) is read from HBM once per launch, not per batch
+    const long long batches = n_items / splits;
+    const long long p0 = (item % batches) * B;
+    const int split = static_cast<int>(item / batches);
     const int n_valid = static_cast<int>(min(static_cast<long long>(B), n_perm - p0));
 
     // ---- stage the inverse permutations: T[perm[k]][q] = k (B independent loads in flight) ----
