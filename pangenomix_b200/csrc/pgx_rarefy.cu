@@ -11,19 +11,23 @@
 // of both histograms is a column sum of the table (closed form); the row kernels only ever
 // produce the ONE non-zero statistic of every (gene, permutation).
 //
-// Kernel 1 (list_kernel<B>): genes with a short list.  A CTA stages the rank tables of B
-//   permutations in shared memory as T[genome][B] uint16 -- one 16-byte line per genome for
-//   B = 8 -- and its warps pull tasks of 32 rows, one lane per row.  Every index costs ONE
-//   shared-memory gather that serves all B permutations, folded into packed uint16x2
-//   running minima (VIMNMX.U16x2).  The host ordered the indices of a row so that the
-//   lanes of a wavefront hit distinct banks.  If the min is 0 the wanted statistic is the
-//   mex of the list's ranks instead (probe genomes in rank order against the sorted copy).
-// Kernel 2 (probe_kernel): genes with long lists, stored as a genome-major, bit-sliced
-//   bitmap (32 genes per word).  A warp walks one genome order for 1,024 genes at once, one
-//   coalesced 128-byte line per step; the first genome whose bit differs from the rank-0
-//   genome's bit is the gene's statistic.  O(N / m) steps instead of O(m) gathers.
+// Kernel 1 (list_kernel<B>): genes with a short list.  Persistent CTAs; per item a CTA stages the
+//   rank tables of B permutations in shared memory as T[genome][B] uint16 -- one 16-byte line
+//   per genome for B = 8 -- and its warps stream runs of sub-blocks of 32 rows, one lane per row,
+//   4 chunk loads in flight.  Every index costs ONE shared-memory gather that serves all B
+//   permutations, folded into packed uint16x2 running minima (VIMNMX.U16x2).  The host ordered
+//   the indices of a row so that the lanes of a wavefront hit distinct banks.  If the min is 0
+//   the wanted statistic is the mex of the list's ranks instead: such (row, permutation) events
+//   are queued per warp and resolved 32 at a time against the sorted copy of the lists.
+// Kernel 2 (probe_kernel<W>): genes with long lists, stored as a genome-major, bit-sliced
+//   bitmap (32 genes per word).  A warp walks one genome order for 1,024 W genes at once, one
+//   coalesced line of 128 W bytes per step; the first genome whose bit differs from the rank-0
+//   genome's bit is the gene's statistic.  O(N / m) steps instead of O(m) gathers.  It runs
+//   beside kernel 1 on a second stream (shared-memory-pipe bound vs issue bound).
 // Kernel 3 (scan_kernel): adds the closed-form gene classes and turns each histogram into
 //   its curve with a block-wide prefix scan, in place.
+// Host entry points at the end of the file: the device-pointer calls, the host-buffer pipeline
+// (pgx_pan_core_curves_host) and the reference's whole loop in one call (pgx_estimate_pan_core).
 #include <stdlib.h>
 #include <string.h>
 #include <sys/mman.h>
