@@ -32,7 +32,7 @@ def needs_build():
     return any(os.path.getmtime(d) > built for d in deps)
 
 
-def build(force=False, verbose=False):
+def build(force=False, verbose=False, debug=False):
     if not force and not needs_build():
         return LIB
     objects = []
@@ -46,10 +46,13 @@ def build(force=False, verbose=False):
            "-I", os.path.join(REPO, "include"), "-I", CSRC, "-o", LIB]
     if verbose:
         cmd += ["-Xptxas", "-v"]
+    if debug:
+        cmd += ["-DPGX_DEBUG_BOUNDS"]          # device-side index assertions (see pgx_common.cuh)
     cmd += [os.path.join(CSRC, s) for s in SOURCES] + objects
     subprocess.run(cmd, check=True)
     return LIB
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv or "--debug" in sys.argv, verbose="--verbose" in sys.argv,
+                debug="--debug" in sys.argv))

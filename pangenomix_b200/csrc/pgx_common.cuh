@@ -36,6 +36,21 @@ int fail(int code, const char *fmt, ...);
 
 constexpr unsigned FULL_MASK = 0xffffffffu;
 
+// Device-side bounds checks for debug builds (python -m pangenomix_b200.build --debug): compute-sanitizer
+// is not available on every pool, so index invariants of the kernels can be asserted instead.
+#ifdef PGX_DEBUG_BOUNDS
+#define PGX_DEVICE_CHECK(cond)                                                                  \
+    do {                                                                                        \
+        if (!(cond)) {                                                                          \
+            printf("PGX_DEVICE_CHECK failed: %s (%s:%d) block %d thread %d\n", #cond, __FILE__, __LINE__, \
+                   static_cast<int>(blockIdx.x), static_cast<int>(threadIdx.x));                \
+            __trap();                                                                           \
+        }                                                                                       \
+    } while (0)
+#else
+#define PGX_DEVICE_CHECK(cond) do { } while (0)
+#endif
+
 // 128-bit streaming load: the folded index chunks are read once per CTA pass and must
 // not displace the rank table's neighbours in L1.
 __device__ __forceinline__ uint4 ldg_stream(const uint4 *ptr)

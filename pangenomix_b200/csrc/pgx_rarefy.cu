@@ -178,6 +178,7 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
     // mex of one queued (row, permutation): all lanes of the warp work on different events
     auto resolve = [&](uint32_t ev) {
         const int q = ev & 7, row = ev >> 4;
+        PGX_DEVICE_CHECK(row < plan.n_rows && q < n_valid);
         const int s0 = plan.d_sorted_ptr[row];
         const int k = mex_probe(perms + (p0 + q) * n, plan.d_sorted_idx + s0, plan.d_sorted_ptr[row + 1] - s0, n);
         // present list: min -> pan histogram, mex -> core histogram; absent list: swapped.
@@ -196,6 +197,8 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
         const int n_rows = td.w;
         const int total = ((n_rows + 31) >> 5) * nch;
         const uint4 *cp = chunks + td.x + lane;
+        PGX_DEVICE_CHECK(td.x >= 0 && static_cast<long long>(td.x) + static_cast<long long>(total) * 32 <= plan.n_chunks);
+        PGX_DEVICE_CHECK(td.z >= 0 && td.z + n_rows <= plan.n_rows);
         int32_t *list_hist = hist + (absent_list ? n : 0);
 
         uint4 buf[LIST_DEPTH];
@@ -211,6 +214,10 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
 #pragma unroll
             for (int d = 0; d + 1 < LIST_DEPTH; ++d) buf[d] = buf[d + 1];
             if (s + LIST_DEPTH < total) buf[LIST_DEPTH - 1] = ldg_stream(cp + (s + LIST_DEPTH) * 32);
+            PGX_DEVICE_CHECK((cur.x & 0xffffu) < static_cast<uint32_t>(n + SENTINELS) && (cur.x >> 16) < static_cast<uint32_t>(n + SENTINELS) &&
+                             (cur.y & 0xffffu) < static_cast<uint32_t>(n + SENTINELS) && (cur.y >> 16) < static_cast<uint32_t>(n + SENTINELS) &&
+                             (cur.z & 0xffffu) < static_cast<uint32_t>(n + SENTINELS) && (cur.z >> 16) < static_cast<uint32_t>(n + SENTINELS) &&
+                             (cur.w & 0xffffu) < static_cast<uint32_t>(n + SENTINELS) && (cur.w >> 16) < static_cast<uint32_t>(n + SENTINELS));
             gather_chunk<B>(table, cur, acc);
             if (--left) continue;
 
@@ -222,12 +229,14 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
                     uint32_t mn;
                     if constexpr (B == 1) mn = acc[0] & 0xffffu;
                     else mn = (acc[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
+                    PGX_DEVICE_CHECK(!valid || mn < static_cast<uint32_t>(n));          // a real row always holds a genome
                     if (valid && mn != 0) atomicAdd(list_hist + (p0 + q) * row_stride + mn, 1);
                     // min == 0: the wanted statistic is the mex; queue it, resolve 32 at a time
                     const bool ev = valid && mn == 0;
                     const uint32_t m = __ballot_sync(FULL_MASK, ev);
                     if (m) {
-                        if (ev) queue[queued + __popc(m & ((1u << lane) - 1u))] =
+                        PGX_DEVICE_CHECK(queued + __popc(m) <= EVENT_QUEUE);
+                    if (ev) queue[queued + __popc(m & ((1u << lane) - 1u))] =
                             (static_cast<uint32_t>(row) << 4) | (absent_list << 3) | q;
                         queued += __popc(m);
                         __syncwarp();
@@ -326,6 +335,7 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
 #pragma unroll
             for (int j = 0; j < DEPTH; ++j) {
                 const uint32_t c = __shfl_sync(FULL_MASK, chunk, j0 + j);
+                PGX_DEVICE_CHECK(c < static_cast<uint32_t>(n));
                 load_line<W>(lines + static_cast<size_t>(c) * (32 * W), d[j]);
 #pragma unroll
                 for (int x = 0; x < W; ++x) {
@@ -353,6 +363,7 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
                 }
                 const uint32_t total = __reduce_add_sync(FULL_MASK, packed);     // <= 4,096 per half
                 const uint32_t mine = lane == 1 ? total >> 16 : total & 0xffffu;
+                PGX_DEVICE_CHECK(k0 + j0 + j > 0 && k0 + j0 + j < n);
                 if (lane < 2 && mine) atomicAdd(out + (k0 + j0 + j), static_cast<int>(mine));
             }
             uint32_t left = 0;
@@ -361,6 +372,7 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
             if (!__any_sync(FULL_MASK, left)) return;
         }
     }
+    PGX_DEVICE_CHECK(false && "a bitmap row never flipped: it is empty or universal and must not be in the bitmap");
 }
 
 // Histogram -> curve, in place when OutT == int32_t and out == hist.
