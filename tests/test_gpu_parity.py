@@ -77,6 +77,29 @@ def test_drop_in_api_frame_rng_and_heaps(engine_mod, name, capsys):
     assert list(fit_it.columns) == ["alpha", "kappa"] and fit_it.index[0] == "Iter1"
 
 
+def test_npz_written_by_the_reference_to_curves(engine_mod, capsys):
+    """The whole user path of README.md:146-176 on the file the REFERENCE's own writer produced
+    (tests/golden/lsdf_small.npz): read_lsdf -> estimate_pan_core_size -> calculate_mean -> fit_heaps,
+    against the curves and fits the live reference computed from the same table and seed."""
+    import os
+    from conftest import GOLDEN
+    from pangenomix_b200 import pangenome_analysis as pa, plot, sparse_utils as su
+    g = load_golden("synth_800x50_s0")
+    lsdf = su.read_lsdf(os.path.join(GOLDEN, "lsdf_small.npz"))
+    assert lsdf.shape == (800, 50)
+    np.random.seed(int(g["seed"]))
+    df = pa.estimate_pan_core_size(lsdf, int(g["num_iter"]))
+    capsys.readouterr()
+    assert np.array_equal(df.values, g["curves"].astype(np.float64))
+    mean = plot.calculate_mean(df)
+    assert np.array_equal(mean.values[0], g["mean"])
+    np.testing.assert_allclose(pa.fit_heaps_by_iteration(mean).values[0], g["heaps_mean"], rtol=1e-12)
+    # a second call on the same LSDF object reuses the uploaded table
+    np.random.seed(int(g["seed"]))
+    assert np.array_equal(pa.estimate_pan_core_size(lsdf, 3).values, g["curves"][:3].astype(np.float64))
+    capsys.readouterr()
+
+
 def _mixed_matrix(n, seed=5, per_class=24):
     rng = np.random.RandomState(seed)
     dens = np.concatenate([np.full(per_class, d) for d in
