@@ -193,6 +193,24 @@ def test_random_tables_every_layout_choice(engine_mod):
         _native.set_tuning(0, 0, 0)
 
 
+def test_many_permutations_in_one_call(engine_mod):
+    """70,001 permutations in ONE call (more than 65,535 batches of the old grid limit would allow, an odd
+    count, several host-path blocks): oracle parity on a sample, invariants on all."""
+    coo = _mixed_matrix(60, seed=4, per_class=30)
+    eng = engine_mod.PanCoreEngine(coo, long_threshold=6)
+    assert eng.host_plan.n_long > 0 and eng.host_plan.n_rows > 0
+    rng = np.random.RandomState(8)
+    perms = np.argsort(rng.random_sample((70001, 60)), axis=1).astype(np.uint16)
+    curves = eng.curves_host(perms)
+    sample = [0, 1, 7, 8, 65535, 65536, 69999, 70000]
+    assert np.array_equal(curves[sample], _oracle_curves(coo, perms[sample]))
+    pan, core = curves[:, :60], curves[:, 60:]
+    assert np.all(np.diff(pan, axis=1) >= 0) and np.all(np.diff(core, axis=1) <= 0)
+    assert np.array_equal(pan[:, 0], core[:, 0])
+    col_sums = np.asarray(coo.sum(axis=0)).ravel()
+    assert np.array_equal(pan[:, 0], col_sums[perms[:, 0]])
+
+
 def test_degenerate_shapes(engine_mod):
     import torch
     # no folded rows at all: everything is a closed form
