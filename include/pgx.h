@@ -184,6 +184,25 @@ int pgx_plan_build_bitmap(const int64_t *indptr, const int32_t *indices, const i
                           int64_t n_long, int32_t n_genomes, int32_t slice_words, uint32_t *bits,
                           int32_t n_threads);
 
+/* Host-side helpers of the planner for the table ingest (no GPU work; threaded; n_threads 0 = choose).
+ * They do what pangenome_analysis.py:74-75 asks of scipy (``df_genes.data`` COO -> compressed rows), gene-major.
+ *
+ * pgx_plan_coo_to_csr: COO entries (row = gene, col = genome; every stored value 1 -- the caller checks) ->
+ *   canonical CSR: indptr int64 [n_genes + 1], indices int32 [nnz] ascending inside a row, colsum int32
+ *   [n_genomes].  Duplicate (gene, genome) pairs are kept and counted in *n_duplicates (scipy's tocsr would
+ *   sum them to 2, a non-binary table: the caller rejects it).
+ * pgx_plan_folded_lists: for list row r (gene genes[r]) the ascending list of its present genomes
+ *   (use_abs[r] == 0) or absent genomes (use_abs[r] != 0) into flat[ptr[r] .. ptr[r + 1]).
+ * pgx_plan_missing_genome: missing[r] = the one genome gene genes[r] (present in N - 1 genomes) lacks. */
+int pgx_plan_coo_to_csr(const int32_t *row, const int32_t *col, int64_t nnz, int32_t n_genes, int32_t n_genomes,
+                        int64_t *indptr, int32_t *indices, int32_t *colsum, int64_t *n_duplicates,
+                        int32_t n_threads);
+int pgx_plan_folded_lists(const int64_t *indptr, const int32_t *indices, const int64_t *genes,
+                          const uint8_t *use_abs, const int64_t *ptr, int64_t n_rows, int32_t n_genomes,
+                          int32_t *flat, int32_t n_threads);
+int pgx_plan_missing_genome(const int64_t *indptr, const int32_t *indices, const int64_t *genes, int64_t n_rows,
+                            int32_t n_genomes, int32_t *missing, int32_t n_threads);
+
 /* numpy legacy RandomState stream (host): ``count`` consecutive
  * ``a = np.arange(n); np.random.shuffle(a)`` results as uint16 rows, continuing from the
  * MT19937 state in ``mt_key`` (624 words) / ``mt_pos`` exactly as

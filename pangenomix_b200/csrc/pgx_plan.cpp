@@ -12,6 +12,8 @@
 
 #include <algorithm>
 #include <atomic>
+#include <memory>
+#include <new>
 #include <thread>
 #include <vector>
 
@@ -245,5 +247,241 @@ extern "C" int pgx_plan_build_bitmap(const int64_t *indptr, const int32_t *indic
     work();
     for (auto &th : pool) th.join();
     if (bad.load()) return pgx::fail(PGX_ERR_INVALID, "genome index out of range in pgx_plan_build_bitmap");
+    return PGX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Table ingest: ``df_genes.data`` (scipy COO, gene x genome) -> canonical gene-major CSR, the
+// folded lists of the list rows and the missing genome of the single-absence rows.  These replace
+// scipy's single-threaded coo_tocsr / sum_duplicates / sort_indices and a few O(nnz) numpy
+// gathers of plan.py (which stay as the specification, PGX_PLAN_NUMPY=1) with threaded loops.
+// ---------------------------------------------------------------------------------------------
+namespace {
+
+int host_threads(int32_t wanted, long long units)
+{
+    int threads = wanted > 0 ? wanted : static_cast<int>(std::min(16u, std::max(1u, std::thread::hardware_concurrency())));
+    return static_cast<int>(std::max<long long>(1, std::min<long long>(threads, units)));
+}
+
+template <typename F>
+void run_threads(int threads, F &&body)
+{
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t) pool.emplace_back([&body, t]() { body(t); });
+    body(0);
+    for (auto &th : pool) th.join();
+}
+
+}  // namespace
+
+// COO of a BINARY table (every stored value is 1; the caller checks) -> CSR with sorted rows, as a
+// two-level counting sort that keeps the input order inside a gene (column-sorted input -- what the
+// reference's producers and scipy's own conversions emit -- then needs no sorting afterwards):
+//   pass 0  every thread histograms its slice of the entries over blocks of 2^shift genes (<= 512 blocks);
+//   pass A  every thread appends its entries, packed as (gene - block start) << 16 | genome, to its own
+//           part of each block of a temporary array: a few hundred sequential write streams per thread;
+//   pass B  blocks are handed out to the threads: count per gene, prefix, scatter -- the write set of a
+//           block is one cache line per gene, cache-resident -- then a sortedness / duplicate check per
+//           gene and the column sums.
+// Duplicate (gene, genome) pairs are kept and counted in *n_duplicates: scipy would sum them to 2, i.e.
+// a non-binary table.
+extern "C" int pgx_plan_coo_to_csr(const int32_t *row, const int32_t *col, int64_t nnz, int32_t n_genes,
+                                   int32_t n_genomes, int64_t *indptr, int32_t *indices, int32_t *colsum,
+                                   int64_t *n_duplicates, int32_t n_threads)
+{
+    if (nnz < 0 || n_genes < 0 || n_genomes < 0) return pgx::fail(PGX_ERR_INVALID, "negative size passed to pgx_plan_coo_to_csr");
+    if (n_genomes > 65536) return pgx::fail(PGX_ERR_UNSUPPORTED, "pgx_plan_coo_to_csr packs genome indices in 16 bits");
+    if (!indptr || !colsum || !n_duplicates || (nnz > 0 && (!row || !col || !indices)))
+        return pgx::fail(PGX_ERR_INVALID, "null pointer passed to pgx_plan_coo_to_csr");
+    *n_duplicates = 0;
+    std::fill(colsum, colsum + n_genomes, 0);
+    std::fill(indptr, indptr + n_genes + 1, 0);
+    if (nnz == 0) return PGX_OK;
+    if (n_genes == 0) return pgx::fail(PGX_ERR_INVALID, "entries in a table without genes");
+    int shift = 6;
+    while (shift < 16 && ((static_cast<int64_t>(n_genes) + (1ll << shift) - 1) >> shift) > 512) ++shift;
+    const int64_t n_blocks = (static_cast<int64_t>(n_genes) + (1ll << shift) - 1) >> shift;
+    const int threads = host_threads(n_threads, std::max<long long>(1, nnz / (1 << 16)));
+    std::vector<int64_t> hist(static_cast<size_t>(threads) * n_blocks, 0);      // [thread][block], then write offsets
+    std::vector<int64_t> block_start(n_blocks + 1, 0);
+    std::atomic<int> bad{0};
+    auto slice = [&](int t, int64_t *lo, int64_t *hi) {
+        *lo = nnz * t / threads;
+        *hi = nnz * (t + 1) / threads;
+    };
+    run_threads(threads, [&](int t) {
+        int64_t lo, hi;
+        slice(t, &lo, &hi);
+        int64_t *h = hist.data() + static_cast<size_t>(t) * n_blocks;
+        bool oob = false;
+        for (int64_t i = lo; i < hi; ++i) {
+            const uint32_t r = static_cast<uint32_t>(row[i]);
+            if (r >= static_cast<uint32_t>(n_genes)) {
+                oob = true;
+                continue;
+            }
+            ++h[r >> shift];
+        }
+        if (oob) bad.store(1);
+    });
+    if (bad.load()) return pgx::fail(PGX_ERR_INVALID, "gene index out of range in the COO table");
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        int64_t at = block_start[b];
+        for (int t = 0; t < threads; ++t) {
+            const int64_t c = hist[static_cast<size_t>(t) * n_blocks + b];
+            hist[static_cast<size_t>(t) * n_blocks + b] = at;
+            at += c;
+        }
+        block_start[b + 1] = at;
+    }
+    std::unique_ptr<uint32_t[]> packed(new (std::nothrow) uint32_t[static_cast<size_t>(nnz)]);
+    if (!packed) return pgx::fail(PGX_ERR_INVALID, "out of host memory in pgx_plan_coo_to_csr");
+    run_threads(threads, [&](int t) {
+        int64_t lo, hi;
+        slice(t, &lo, &hi);
+        int64_t *at = hist.data() + static_cast<size_t>(t) * n_blocks;
+        const uint32_t low = (1u << shift) - 1;
+        bool oob = false;
+        for (int64_t i = lo; i < hi; ++i) {
+            const uint32_t r = static_cast<uint32_t>(row[i]), c = static_cast<uint32_t>(col[i]);
+            if (c >= static_cast<uint32_t>(n_genomes)) {
+                oob = true;
+                continue;
+            }
+            packed[at[r >> shift]++] = (r & low) << 16 | c;
+        }
+        if (oob) bad.store(1);
+    });
+    if (bad.load()) return pgx::fail(PGX_ERR_INVALID, "genome index out of range in the COO table");
+    std::vector<std::vector<int32_t>> part_colsum(threads);
+    std::atomic<long long> next{0}, dups{0};
+    run_threads(threads, [&](int t) {
+        std::vector<int32_t> &cs = part_colsum[t];
+        cs.assign(n_genomes, 0);
+        std::vector<int64_t> pos(static_cast<size_t>(1) << shift);
+        long long d = 0;
+        for (;;) {
+            const long long b = next.fetch_add(1);
+            if (b >= n_blocks) break;
+            const int64_t g0 = b << shift, g1 = std::min<int64_t>(n_genes, g0 + (1ll << shift));
+            const uint32_t *src = packed.get() + block_start[b], *end = packed.get() + block_start[b + 1];
+            std::fill(pos.begin(), pos.end(), 0);
+            for (const uint32_t *p = src; p < end; ++p) ++pos[*p >> 16];
+            int64_t at = block_start[b];
+            for (int64_t g = g0; g < g1; ++g) {
+                const int64_t c = pos[g - g0];
+                pos[g - g0] = at;
+                indptr[g + 1] = at + c;          // indptr[g0] is written by the previous block (or is indptr[0] = 0)
+                at += c;
+            }
+            for (const uint32_t *p = src; p < end; ++p) {
+                const uint32_t c = *p & 0xffffu;
+                indices[pos[*p >> 16]++] = static_cast<int32_t>(c);
+                ++cs[c];
+            }
+            for (int64_t g = g0; g < g1; ++g) {
+                int32_t *a = indices + (g == g0 ? block_start[b] : indptr[g]), *e = indices + indptr[g + 1];
+                bool sorted = true;
+                for (int32_t *p = a + 1; p < e; ++p) {
+                    if (p[0] <= p[-1]) {
+                        sorted = false;
+                        break;
+                    }
+                }
+                if (!sorted) {
+                    std::sort(a, e);
+                    for (int32_t *p = a + 1; p < e; ++p) d += p[0] == p[-1];
+                }
+            }
+        }
+        dups.fetch_add(d);
+    });
+    for (int t = 0; t < threads; ++t)
+        for (size_t c = 0; c < part_colsum[t].size(); ++c) colsum[c] += part_colsum[t][c];
+    *n_duplicates = dups.load();
+    return PGX_OK;
+}
+
+// plan._folded_lists: row r of the list rows is gene genes[r]; its folded list -- the present genomes
+// (use_abs[r] == 0) or the absent ones -- goes to flat[ptr[r] .. ptr[r + 1]), ascending.
+extern "C" int pgx_plan_folded_lists(const int64_t *indptr, const int32_t *indices, const int64_t *genes,
+                                     const uint8_t *use_abs, const int64_t *ptr, int64_t n_rows,
+                                     int32_t n_genomes, int32_t *flat, int32_t n_threads)
+{
+    if (n_rows < 0 || n_genomes < 1) return pgx::fail(PGX_ERR_INVALID, "bad shape passed to pgx_plan_folded_lists");
+    if (n_rows == 0) return PGX_OK;
+    if (!indptr || !genes || !use_abs || !ptr || (ptr[n_rows] > 0 && (!indices || !flat)))
+        return pgx::fail(PGX_ERR_INVALID, "null pointer passed to pgx_plan_folded_lists");
+    const long long grain = 512;
+    std::atomic<long long> next{0};
+    std::atomic<int> bad{0};
+    const int threads = host_threads(n_threads, (n_rows + grain - 1) / grain);
+    run_threads(threads, [&](int) {
+        for (;;) {
+            const long long r0 = next.fetch_add(grain);
+            if (r0 >= n_rows) return;
+            const long long r1 = std::min<long long>(n_rows, r0 + grain);
+            for (long long r = r0; r < r1; ++r) {
+                const int32_t *a = indices + indptr[genes[r]], *e = indices + indptr[genes[r] + 1];
+                int32_t *out = flat + ptr[r];
+                const long long want = ptr[r + 1] - ptr[r];
+                if (!use_abs[r]) {
+                    if (e - a != want) {
+                        bad.store(1);
+                        continue;
+                    }
+                    memcpy(out, a, sizeof(int32_t) * static_cast<size_t>(want));
+                } else {
+                    if (n_genomes - (e - a) != want) {
+                        bad.store(1);
+                        continue;
+                    }
+                    int32_t c = 0;
+                    for (const int32_t *p = a; p < e; ++p) {
+                        for (; c < *p; ++c) *out++ = c;
+                        c = *p + 1;
+                    }
+                    for (; c < n_genomes; ++c) *out++ = c;
+                    if (out != flat + ptr[r + 1]) bad.store(1);       // unsorted or duplicated input
+                }
+            }
+        }
+    });
+    if (bad.load()) return pgx::fail(PGX_ERR_INVALID, "inconsistent rows passed to pgx_plan_folded_lists");
+    return PGX_OK;
+}
+
+// The one genome every gene of ``genes`` (present in exactly N - 1 genomes) is absent from.
+extern "C" int pgx_plan_missing_genome(const int64_t *indptr, const int32_t *indices, const int64_t *genes,
+                                       int64_t n_rows, int32_t n_genomes, int32_t *missing, int32_t n_threads)
+{
+    if (n_rows < 0 || n_genomes < 1) return pgx::fail(PGX_ERR_INVALID, "bad shape passed to pgx_plan_missing_genome");
+    if (n_rows == 0) return PGX_OK;
+    if (!indptr || !indices || !genes || !missing) return pgx::fail(PGX_ERR_INVALID, "null pointer passed to pgx_plan_missing_genome");
+    const long long grain = std::max<long long>(1, (1 << 20) / n_genomes);
+    std::atomic<long long> next{0};
+    std::atomic<int> bad{0};
+    const long long all = static_cast<long long>(n_genomes) * (n_genomes - 1) / 2;
+    const int threads = host_threads(n_threads, (n_rows + grain - 1) / grain);
+    run_threads(threads, [&](int) {
+        for (;;) {
+            const long long r0 = next.fetch_add(grain);
+            if (r0 >= n_rows) return;
+            const long long r1 = std::min<long long>(n_rows, r0 + grain);
+            for (long long r = r0; r < r1; ++r) {
+                const int64_t a = indptr[genes[r]], e = indptr[genes[r] + 1];
+                long long sum = 0;
+                for (int64_t i = a; i < e; ++i) sum += indices[i];
+                const long long miss = all - sum;
+                if (e - a != n_genomes - 1 || miss < 0 || miss >= n_genomes) {
+                    bad.store(1);
+                    continue;
+                }
+                missing[r] = static_cast<int32_t>(miss);
+            }
+        }
+    });
+    if (bad.load()) return pgx::fail(PGX_ERR_INVALID, "rows passed to pgx_plan_missing_genome are not single-absence rows");
     return PGX_OK;
 }

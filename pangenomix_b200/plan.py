@@ -174,6 +174,46 @@ def gene_major_csr(data):
     return csr
 
 
+def _numpy_spec():
+    """PGX_PLAN_NUMPY=1 plans with the numpy specification instead of libpgx's threaded host helpers."""
+    import os
+    return os.environ.get("PGX_PLAN_NUMPY") == "1"
+
+
+def canonical_csr(data):
+    """(indptr int64 [G + 1], indices int32 [nnz] ascending per gene, colsum int32 [N], (G, N)) of the table.
+
+    The usual input -- a COO matrix whose stored values are all 1, as every producer of the reference
+    writes it (pangenome.py:631-650) -- goes through libpgx's threaded host helper pgx_plan_coo_to_csr;
+    anything else (other formats, other values, duplicate entries, PGX_PLAN_NUMPY=1) through
+    ``gene_major_csr``, the scipy specification with the reference's duplicate-summing semantics.
+    """
+    if (not _numpy_spec() and scipy.sparse.issparse(data) and data.format == "coo" and data.ndim == 2
+            and 0 < data.shape[1] <= MAX_GENOMES and data.shape[0] < 2 ** 31 - 1 and data.nnz > 0):
+        values = np.asarray(data.data)
+        if values.dtype != object and bool(np.all(values == 1)):
+            from . import _native
+            import ctypes
+            n_genes, n = (int(v) for v in data.shape)
+            row = np.ascontiguousarray(data.row, dtype=np.int32)
+            col = np.ascontiguousarray(data.col, dtype=np.int32)
+            nnz = int(row.shape[0])
+            indptr = np.empty(n_genes + 1, dtype=np.int64)
+            indices = np.empty(nnz, dtype=np.int32)
+            colsum = np.empty(n, dtype=np.int32)
+            dups = ctypes.c_int64(0)
+            _native.check(_native.load().pgx_plan_coo_to_csr(
+                row.ctypes.data, col.ctypes.data, nnz, n_genes, n, indptr.ctypes.data, indices.ctypes.data,
+                colsum.ctypes.data, ctypes.byref(dups), 0))
+            if dups.value == 0:
+                return indptr, indices, colsum, (n_genes, n)
+            # duplicates: let the specification decide (they sum to 2 -> rejected as non-binary)
+    csr = gene_major_csr(data)
+    indices = np.asarray(csr.indices)
+    colsum = np.bincount(indices, minlength=csr.shape[1]).astype(np.int32)
+    return csr.indptr.astype(np.int64), indices, colsum, tuple(int(v) for v in csr.shape)
+
+
 def _segment_positions(lengths):
     """For concatenated segments of the given lengths: position of every element in its segment."""
     total = int(lengths.sum())
@@ -182,9 +222,20 @@ def _segment_positions(lengths):
 
 
 def _folded_lists(indptr, indices, m, genes, use_abs, length, n):
-    """Concatenated sorted folded lists of ``genes`` (present or absent genomes), int32."""
+    """Concatenated sorted folded lists of ``genes`` (present or absent genomes), int32.  Host helper
+    pgx_plan_folded_lists; PGX_PLAN_NUMPY=1 selects the numpy specification below."""
     ptr = np.concatenate(([0], np.cumsum(length))).astype(np.int64)
     flat = np.empty(int(ptr[-1]), dtype=np.int32)
+    if not _numpy_spec() and genes.size:
+        from . import _native
+        ip = np.ascontiguousarray(indptr, dtype=np.int64)
+        ix = np.ascontiguousarray(indices, dtype=np.int32)
+        gs = np.ascontiguousarray(genes, dtype=np.int64)
+        ua = np.ascontiguousarray(use_abs, dtype=np.uint8)
+        _native.check(_native.load().pgx_plan_folded_lists(
+            ip.ctypes.data, ix.ctypes.data, gs.ctypes.data, ua.ctypes.data, ptr.ctypes.data, gs.shape[0], int(n),
+            flat.ctypes.data, 0))
+        return flat, ptr
     keep = np.flatnonzero(~use_abs)
     if keep.size:
         lens = length[keep]
@@ -208,6 +259,22 @@ def _folded_lists(indptr, indices, m, genes, use_abs, length, n):
             dst = np.repeat(ptr[:-1][rows], lens) + _segment_positions(lens)
             flat[dst] = cols
     return flat, ptr
+
+
+def _missing_genome(indptr, indices, genes, n):
+    """The genome every gene of ``genes`` (present in exactly n - 1 genomes) is absent from.  Host helper
+    pgx_plan_missing_genome; PGX_PLAN_NUMPY=1 selects the numpy specification (prefix sums of the indices)."""
+    if _numpy_spec():
+        csum = np.concatenate(([0], np.cumsum(indices, dtype=np.int64)))
+        return n * (n - 1) // 2 - (csum[indptr[genes + 1]] - csum[indptr[genes]])
+    from . import _native
+    ip = np.ascontiguousarray(indptr, dtype=np.int64)
+    ix = np.ascontiguousarray(indices, dtype=np.int32)
+    gs = np.ascontiguousarray(genes, dtype=np.int64)
+    missing = np.empty(gs.shape[0], dtype=np.int32)
+    _native.check(_native.load().pgx_plan_missing_genome(
+        ip.ctypes.data, ix.ctypes.data, gs.ctypes.data, gs.shape[0], int(n), missing.ctypes.data, 0))
+    return missing
 
 
 def _colour_groups(cnt, n_steps):
@@ -352,10 +419,9 @@ def _bank_ordered_chunks_numpy(flat, ptr, block_first, block_nch, block_first_ro
 def _build_bitmap(indptr, indices, m, long_gene, n, slice_words):
     """Genome-major bit-sliced bitmap of the long rows (include/pgx.h, d_bits).  Host helper
     pgx_plan_build_bitmap; PGX_PLAN_NUMPY=1 selects the numpy specification (dense block + packbits)."""
-    import os
     sb_rows = SLICE_ROWS * slice_words
     n_super = (long_gene.size + sb_rows - 1) // sb_rows
-    if os.environ.get("PGX_PLAN_NUMPY") == "1":
+    if _numpy_spec():
         bits = np.zeros((n_super, n, sb_rows // 32), dtype=np.uint32)
         for sb in range(n_super):
             rows = long_gene[sb * sb_rows:(sb + 1) * sb_rows]
@@ -379,8 +445,7 @@ def _bank_ordered_chunks(flat, ptr, block_first, block_nch, block_first_row, blo
     """The bank ordering through libpgx's host helper pgx_plan_bank_order (csrc/pgx_plan.cpp: the same
     algorithm as ``_bank_ordered_chunks_numpy`` with identical output, as plain threaded loops);
     PGX_PLAN_NUMPY=1 selects the numpy specification instead."""
-    import os
-    if os.environ.get("PGX_PLAN_NUMPY") == "1":
+    if _numpy_spec():
         return _bank_ordered_chunks_numpy(flat, ptr, block_first, block_nch, block_first_row, block_rows, n, modulus)
     from . import _native
     lib = _native.load()
@@ -395,8 +460,10 @@ def _bank_ordered_chunks(flat, ptr, block_first, block_nch, block_first_row, blo
 
 
 def build_host_plan(data, long_threshold=None, perms_per_cta=None, slice_words=None) -> HostPlan:
-    csr = gene_major_csr(data)
-    n_genes, n = csr.shape
+    if scipy.sparse.issparse(data) and data.ndim == 2 and data.shape[1] > MAX_GENOMES:
+        raise ValueError("n_genomes = %d exceeds the supported maximum of %d" % (data.shape[1], MAX_GENOMES))
+    indptr, indices, colsum, (n_genes, n) = canonical_csr(data)
+    nnz = int(indices.shape[0])
     if n < 1:
         raise ValueError("table has no genome columns")
     if n > MAX_GENOMES:
@@ -411,10 +478,7 @@ def build_host_plan(data, long_threshold=None, perms_per_cta=None, slice_words=N
     if long_threshold is None:
         long_threshold = default_long_threshold(n)
     long_threshold = int(long_threshold)
-    indptr = csr.indptr.astype(np.int64)
-    indices = csr.indices
     m = np.diff(indptr)
-    colsum = np.bincount(indices, minlength=n).astype(np.int32)
 
     empty = m == 0
     full = (m == n) & ~empty
@@ -424,10 +488,8 @@ def build_host_plan(data, long_threshold=None, perms_per_cta=None, slice_words=N
 
     w_present = np.bincount(indices[indptr[:-1][single_p]], minlength=n).astype(np.int32)
     if single_a.any():
-        csum = np.concatenate(([0], np.cumsum(indices, dtype=np.int64)))
-        row_sum = csum[indptr[1:][single_a]] - csum[indptr[:-1][single_a]]
-        missing = n * (n - 1) // 2 - row_sum
-        w_absent = np.bincount(missing, minlength=n).astype(np.int32)
+        w_absent = np.bincount(_missing_genome(indptr, indices, np.flatnonzero(single_a), n),
+                               minlength=n).astype(np.int32)
     else:
         w_absent = np.zeros(n, dtype=np.int32)
 
@@ -507,7 +569,7 @@ def build_host_plan(data, long_threshold=None, perms_per_cta=None, slice_words=N
         tasks = np.zeros((0, 4), dtype=np.int32)
 
     return HostPlan(
-        n_genes=int(n_genes), n_genomes=int(n), nnz=int(csr.nnz),
+        n_genes=int(n_genes), n_genomes=int(n), nnz=nnz,
         perms_per_cta=int(perms_per_cta), long_threshold=long_threshold,
         colsum=colsum, w_present=w_present, w_absent=w_absent,
         n_empty=int(empty.sum()), n_full=int(full.sum()),

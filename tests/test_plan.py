@@ -148,3 +148,81 @@ def test_plan_random_tables_property():
         assert np.all(got[:, n - 1] == np.count_nonzero(counts)) and np.all(got[:, 2 * n - 1] == np.count_nonzero(counts == n))
 
     check()
+
+
+def _plans_equal(a, b):
+    for f in ("colsum", "w_present", "w_absent", "chunks", "tasks", "sorted_idx", "sorted_ptr", "row_gene",
+              "row_len", "row_absent", "bits", "long_gene"):
+        assert np.array_equal(getattr(a, f), getattr(b, f)), f
+    for f in ("n_genes", "n_genomes", "nnz", "n_empty", "n_full", "nnz_list", "nnz_long", "slice_words"):
+        assert getattr(a, f) == getattr(b, f), f
+
+
+@pytest.mark.parametrize("order", ["column-major", "row-major", "shuffled"])
+@pytest.mark.parametrize("shape", [(360, 700), (5000, 90), (70000, 12)])
+def test_plan_native_ingest_equals_scipy_specification(monkeypatch, order, shape):
+    """pgx_plan_coo_to_csr / pgx_plan_folded_lists / pgx_plan_missing_genome (threaded C++) against the scipy +
+    numpy specification of the same steps: whatever the order of the COO entries, the whole plan is identical.
+    70,000 genes make the counting sort use blocks of 256 genes; (5000, 90) holds single-absence rows."""
+    g, n = shape
+    rng = np.random.RandomState(g + n)
+    dens = rng.choice([0.0, 0.01, 0.05, 0.3, 0.6, 0.95, 0.99, 1.0], size=g)
+    x = rng.random_sample((g, n)) < dens[:, None]
+    row, col = np.nonzero(x.T)[::-1] if order == "column-major" else np.nonzero(x)
+    if order == "shuffled":
+        p = rng.permutation(row.shape[0])
+        row, col = row[p], col[p]
+    coo = scipy.sparse.coo_matrix((np.ones(row.shape[0], dtype=np.int64), (row, col)), shape=shape)
+    native = build_host_plan(coo, long_threshold=9)
+    monkeypatch.setenv("PGX_PLAN_NUMPY", "1")
+    spec = build_host_plan(coo, long_threshold=9)
+    monkeypatch.delenv("PGX_PLAN_NUMPY")
+    _plans_equal(native, spec)
+    assert native.w_absent.sum() > 0 or n > 100
+    # float / bool ones take the same fast path, CSR input the scipy path: same plan
+    _plans_equal(build_host_plan(coo.astype(np.float64), long_threshold=9), spec)
+    _plans_equal(build_host_plan(coo.tocsr(), long_threshold=9), spec)
+
+
+def test_plan_native_ingest_errors_and_corner_cases():
+    import ctypes
+    from pangenomix_b200 import _native
+    from pangenomix_b200.plan import canonical_csr
+    lib = _native.load()
+
+    def call(row, col, g, n):
+        row, col = np.asarray(row, dtype=np.int32), np.asarray(col, dtype=np.int32)
+        indptr, indices = np.empty(g + 1, dtype=np.int64), np.empty(max(1, row.size), dtype=np.int32)
+        colsum, dups = np.empty(n, dtype=np.int32), ctypes.c_int64(-1)
+        rc = lib.pgx_plan_coo_to_csr(row.ctypes.data, col.ctypes.data, row.size, g, n, indptr.ctypes.data,
+                                     indices.ctypes.data, colsum.ctypes.data, ctypes.byref(dups), 3)
+        return rc, indptr, indices[:row.size], colsum, dups.value
+
+    rc, indptr, indices, colsum, dups = call([2, 0, 2, 0], [1, 3, 0, 2], 4, 5)
+    assert rc == 0 and dups == 0
+    assert indptr.tolist() == [0, 2, 2, 4, 4] and indices.tolist() == [2, 3, 0, 1] and colsum.tolist() == [1, 1, 1, 1, 0]
+    assert call([0, 0, 1], [1, 1, 0], 2, 3)[4] == 1                       # a duplicate pair is reported, not merged
+    assert call([0, 2], [0, 0], 2, 3)[0] != 0 and b"gene index" in lib.pgx_last_error()
+    assert call([0, -1], [0, 0], 2, 3)[0] != 0
+    assert call([0, 1], [0, 3], 2, 3)[0] != 0 and b"genome index" in lib.pgx_last_error()
+    assert call([], [], 3, 2)[1].tolist() == [0, 0, 0, 0]
+    # the Python wrapper: duplicates fall back to scipy (summed to 2 -> rejected), zeros are absences
+    with pytest.raises(ValueError):
+        canonical_csr(scipy.sparse.coo_matrix((np.ones(3), ([0, 0, 1], [1, 1, 0])), shape=(2, 3)))
+    indptr, indices, colsum, shape = canonical_csr(
+        scipy.sparse.coo_matrix((np.array([1, 0, 1]), ([0, 0, 1], [0, 1, 2])), shape=(2, 3)))
+    assert indptr.tolist() == [0, 1, 2] and indices.tolist() == [0, 2] and colsum.tolist() == [1, 0, 1] and shape == (2, 3)
+    # folded lists / missing genome reject rows that do not match their descriptors
+    ip, ix = np.array([0, 2, 3], dtype=np.int64), np.array([0, 2, 1], dtype=np.int32)
+    genes, ua = np.array([0, 1], dtype=np.int64), np.array([1, 0], dtype=np.uint8)
+    ptr, flat = np.array([0, 1, 2], dtype=np.int64), np.empty(2, dtype=np.int32)
+    assert lib.pgx_plan_folded_lists(ip.ctypes.data, ix.ctypes.data, genes.ctypes.data, ua.ctypes.data,
+                                     ptr.ctypes.data, 2, 3, flat.ctypes.data, 1) == 0
+    assert flat.tolist() == [1, 1]
+    bad_ptr = np.array([0, 2, 3], dtype=np.int64)
+    assert lib.pgx_plan_folded_lists(ip.ctypes.data, ix.ctypes.data, genes.ctypes.data, ua.ctypes.data,
+                                     bad_ptr.ctypes.data, 2, 3, np.empty(3, dtype=np.int32).ctypes.data, 1) != 0
+    miss = np.empty(2, dtype=np.int32)
+    assert lib.pgx_plan_missing_genome(ip.ctypes.data, ix.ctypes.data, genes.ctypes.data, 1, 3, miss.ctypes.data, 1) == 0
+    assert miss[0] == 1
+    assert lib.pgx_plan_missing_genome(ip.ctypes.data, ix.ctypes.data, genes.ctypes.data, 2, 3, miss.ctypes.data, 1) != 0

@@ -78,3 +78,36 @@ def test_compress_rows_and_sparse_array_round_trip():
     assert frame.shape == (5, 3) and list(frame.index) == list("abcde")
     back = su.sparse_arrays_to_lsdf(frame)
     assert np.array_equal(np.nan_to_num(back.values), x.astype(float))
+
+
+def test_threaded_npz_loader_equals_scipy(tmp_path):
+    """read_lsdf inflates row / col / data of a COO archive on three threads: same matrix, same dtypes,
+    writable arrays as scipy.sparse.load_npz gives; other archives are left to scipy."""
+    ref_file = os.path.join(GOLDEN, "lsdf_small.npz")              # written by the reference's to_npz
+    for path in (ref_file,):
+        fast, slow = su._load_npz_coo(path), scipy.sparse.load_npz(path)
+        assert fast is not None and fast.format == "coo" and fast.shape == slow.shape
+        for name in ("row", "col", "data"):
+            a, b = getattr(fast, name), getattr(slow, name)
+            assert a.dtype == b.dtype and np.array_equal(a, b) and a.flags.writeable
+    coo = synth.bernoulli_matrix(300, 20, 100, seed=2)
+    stored = str(tmp_path / "stored.npz")
+    scipy.sparse.save_npz(stored, coo, compressed=False)
+    assert (su._load_npz_coo(stored).tocsr() != coo.tocsr()).nnz == 0
+    as_csr = str(tmp_path / "csr.npz")
+    scipy.sparse.save_npz(as_csr, coo.tocsr())
+    assert su._load_npz_coo(as_csr) is None                         # not a COO archive: scipy's job
+    labels = "\n".join(["r%d" % i for i in range(300)] + ["c%d" % i for i in range(20)])
+    open(as_csr + ".labels.txt", "w").write(labels)
+    assert su.read_lsdf(as_csr).shape == (300, 20)
+    # a damaged member is not silently accepted
+    blob = bytearray(open(ref_file, "rb").read())
+    import zipfile
+    info = {i.filename: i for i in zipfile.ZipFile(ref_file).infolist()}["row.npy"]
+    blob[info.header_offset + 30 + len("row.npy") + info.compress_size // 2] ^= 0xFF
+    broken = str(tmp_path / "broken.npz")
+    open(broken, "wb").write(bytes(blob))
+    assert su._load_npz_coo(broken) is None
+    import pytest
+    with pytest.raises(Exception):
+        scipy.sparse.load_npz(broken)
