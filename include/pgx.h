@@ -108,7 +108,7 @@ int pgx_pan_core_curves_f64(const pgx_plan *plan, const uint16_t *d_perms, int64
 /* Host-buffer entry point: h_perms [n_perm][N] uint16 and h_curves [n_perm][2N]
  * (int32 when out_f64 == 0, float64 otherwise) live in host memory (pinned memory makes
  * the copies asynchronous).  The plan stays device-resident.  The call pipelines
- * H2D -> kernels -> D2H over two internal streams in blocks of ``perms_per_block``
+ * H2D -> kernels -> D2H over three internal streams in blocks of ``perms_per_block``
  * permutations (0 = choose) and returns when h_curves is complete. */
 int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int64_t n_perm,
                              void *h_curves, int32_t out_f64, int64_t perms_per_block);

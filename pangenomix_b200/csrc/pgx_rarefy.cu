@@ -676,10 +676,13 @@ int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int6
     const size_t hist_bytes = sizeof(int32_t) * 2 * n * block;
     const size_t out_bytes = out_f64 ? sizeof(double) * 2 * n * block : 0;
 
-    cudaStream_t streams[2] = {nullptr, nullptr};
-    uint16_t *d_perms[2] = {nullptr, nullptr};
-    int32_t *d_hist[2] = {nullptr, nullptr};
-    double *d_out[2] = {nullptr, nullptr};
+    // Three slots: while one block's curves travel to the host, the next block's kernels run and the one
+    // after that uploads its permutations, so both PCIe directions and the SMs stay busy.
+    constexpr int SLOTS = 3;
+    cudaStream_t streams[SLOTS] = {nullptr, nullptr, nullptr};
+    uint16_t *d_perms[SLOTS] = {nullptr, nullptr, nullptr};
+    int32_t *d_hist[SLOTS] = {nullptr, nullptr, nullptr};
+    double *d_out[SLOTS] = {nullptr, nullptr, nullptr};
     int rc = PGX_OK;
     // Scratch comes from the device's default memory pool so that repeated calls reuse it.
     {
@@ -691,7 +694,7 @@ int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int6
         }
     }
     auto cleanup = [&]() {
-        for (int s = 0; s < 2; ++s) {
+        for (int s = 0; s < SLOTS; ++s) {
             if (!streams[s]) continue;
             if (d_perms[s]) cudaFreeAsync(d_perms[s], streams[s]);
             if (d_hist[s]) cudaFreeAsync(d_hist[s], streams[s]);
@@ -709,7 +712,7 @@ int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int6
             return rc;                                                                       \
         }                                                                                    \
     } while (0)
-    const int n_streams = n_perm > block ? 2 : 1;
+    const int n_streams = static_cast<int>(std::min<long long>(SLOTS, (n_perm + block - 1) / block));
     for (int s = 0; s < n_streams; ++s) {
         PGX_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
         PGX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_perms[s]), perm_bytes, streams[s]));
@@ -717,7 +720,7 @@ int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int6
         if (out_f64) PGX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_out[s]), out_bytes, streams[s]));
     }
     int slot = 0;
-    for (long long p0 = 0; p0 < n_perm; p0 += block, slot ^= (n_streams - 1)) {
+    for (long long p0 = 0; p0 < n_perm; p0 += block, slot = (slot + 1) % n_streams) {
         const long long np = std::min<long long>(block, n_perm - p0);
         cudaStream_t st = streams[slot];
         PGX_TRY(cudaMemcpyAsync(d_perms[slot], h_perms + p0 * n, sizeof(uint16_t) * n * np,
