@@ -202,6 +202,9 @@ int pgx_plan_folded_lists(const int64_t *indptr, const int32_t *indices, const i
                           int32_t *flat, int32_t n_threads);
 int pgx_plan_missing_genome(const int64_t *indptr, const int32_t *indices, const int64_t *genes, int64_t n_rows,
                             int32_t n_genomes, int32_t *missing, int32_t n_threads);
+/* Returns 1 when every 64-bit word of words[0 .. n) equals ``value``, else 0: the planner's "every stored value
+ * is 1" test for the int64 (value 1) and float64 (value = bits of 1.0) ``data`` arrays of a table. */
+int pgx_plan_all_equal_u64(const uint64_t *words, int64_t n, uint64_t value, int32_t n_threads);
 
 /* numpy legacy RandomState stream (host): ``count`` consecutive
  * ``a = np.arange(n); np.random.shuffle(a)`` results as uint16 rows, continuing from the

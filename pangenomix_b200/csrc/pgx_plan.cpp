@@ -8,7 +8,11 @@
 // sub-blocks, spread over host threads.  It is O(slots) and removes three quarters of the planning
 // time of large tables.  Nothing here touches the GPU.
 #include <stdint.h>
+#include <stdlib.h>
 #include <string.h>
+#if defined(__linux__)
+#include <sys/mman.h>
+#endif
 
 #include <algorithm>
 #include <atomic>
@@ -264,6 +268,26 @@ int host_threads(int32_t wanted, long long units)
     return static_cast<int>(std::max<long long>(1, std::min<long long>(threads, units)));
 }
 
+// Large buffers that are about to be filled for the first time: ask for huge pages (one page fault per
+// 2 MB instead of one per 4 KB; a hint, ignored where transparent huge pages are off).
+void want_huge_pages(void *ptr, size_t bytes)
+{
+#if defined(__linux__) && defined(MADV_HUGEPAGE)
+    if (getenv("PGX_NO_HUGEPAGES")) return;
+    const uintptr_t page = 2u << 20;
+    const uintptr_t lo = (reinterpret_cast<uintptr_t>(ptr) + page - 1) & ~(page - 1);
+    const uintptr_t hi = (reinterpret_cast<uintptr_t>(ptr) + bytes) & ~(page - 1);
+    if (hi > lo) madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
+#else
+    (void)ptr;
+    (void)bytes;
+#endif
+}
+
+struct FreeDeleter {
+    void operator()(void *p) const { free(p); }
+};
+
 template <typename F>
 void run_threads(int threads, F &&body)
 {
@@ -281,9 +305,12 @@ void run_threads(int threads, F &&body)
 //   pass 0  every thread histograms its slice of the entries over blocks of 2^shift genes (<= 512 blocks);
 //   pass A  every thread appends its entries, packed as (gene - block start) << 16 | genome, to its own
 //           part of each block of a temporary array: a few hundred sequential write streams per thread;
-//   pass B  blocks are handed out to the threads: count per gene, prefix, scatter -- the write set of a
-//           block is one cache line per gene, cache-resident -- then a sortedness / duplicate check per
-//           gene and the column sums.
+//   pass B  inside the blocks, again a counting sort, over pieces of at most 2^21 entries so that a block
+//           holding half of the table (the core genes of a pangenome sit next to each other) still spreads
+//           over all threads: count per (piece, gene), prefix per block, scatter per piece -- the write set
+//           of a piece is one cache line per gene of its block, cache-resident;
+//   pass C  per gene (chunks balanced by entries): already ascending?  Otherwise sort -- long rows through a
+//           genome bitmap, short ones with std::sort -- and count duplicates; column sums.
 // Duplicate (gene, genome) pairs are kept and counted in *n_duplicates: scipy would sum them to 2, i.e.
 // a non-binary table.
 extern "C" int pgx_plan_coo_to_csr(const int32_t *row, const int32_t *col, int64_t nnz, int32_t n_genes,
@@ -301,7 +328,8 @@ extern "C" int pgx_plan_coo_to_csr(const int32_t *row, const int32_t *col, int64
     if (n_genes == 0) return pgx::fail(PGX_ERR_INVALID, "entries in a table without genes");
     int shift = 6;
     while (shift < 16 && ((static_cast<int64_t>(n_genes) + (1ll << shift) - 1) >> shift) > 512) ++shift;
-    const int64_t n_blocks = (static_cast<int64_t>(n_genes) + (1ll << shift) - 1) >> shift;
+    const int64_t block_genes = 1ll << shift;
+    const int64_t n_blocks = (static_cast<int64_t>(n_genes) + block_genes - 1) >> shift;
     const int threads = host_threads(n_threads, std::max<long long>(1, nnz / (1 << 16)));
     std::vector<int64_t> hist(static_cast<size_t>(threads) * n_blocks, 0);      // [thread][block], then write offsets
     std::vector<int64_t> block_start(n_blocks + 1, 0);
@@ -335,13 +363,18 @@ extern "C" int pgx_plan_coo_to_csr(const int32_t *row, const int32_t *col, int64
         }
         block_start[b + 1] = at;
     }
-    std::unique_ptr<uint32_t[]> packed(new (std::nothrow) uint32_t[static_cast<size_t>(nnz)]);
-    if (!packed) return pgx::fail(PGX_ERR_INVALID, "out of host memory in pgx_plan_coo_to_csr");
+    void *packed_mem = nullptr;
+    if (posix_memalign(&packed_mem, 2u << 20, sizeof(uint32_t) * static_cast<size_t>(nnz)) != 0 || !packed_mem)
+        return pgx::fail(PGX_ERR_INVALID, "out of host memory in pgx_plan_coo_to_csr");
+    std::unique_ptr<uint32_t, FreeDeleter> packed_owner(static_cast<uint32_t *>(packed_mem));
+    uint32_t *packed = packed_owner.get();
+    want_huge_pages(packed, sizeof(uint32_t) * static_cast<size_t>(nnz));
+    want_huge_pages(indices, sizeof(int32_t) * static_cast<size_t>(nnz));
     run_threads(threads, [&](int t) {
         int64_t lo, hi;
         slice(t, &lo, &hi);
         int64_t *at = hist.data() + static_cast<size_t>(t) * n_blocks;
-        const uint32_t low = (1u << shift) - 1;
+        const uint32_t low = static_cast<uint32_t>(block_genes - 1);
         bool oob = false;
         for (int64_t i = lo; i < hi; ++i) {
             const uint32_t r = static_cast<uint32_t>(row[i]), c = static_cast<uint32_t>(col[i]);
@@ -354,34 +387,87 @@ extern "C" int pgx_plan_coo_to_csr(const int32_t *row, const int32_t *col, int64
         if (oob) bad.store(1);
     });
     if (bad.load()) return pgx::fail(PGX_ERR_INVALID, "genome index out of range in the COO table");
+
+    // pass B: pieces of the blocks
+    struct Piece { int64_t block, lo, hi; };
+    const int64_t piece_entries = 1ll << 21;
+    std::vector<Piece> pieces;
+    std::vector<int64_t> first_piece(n_blocks + 1, 0);
+    for (int64_t b = 0; b < n_blocks; ++b) {
+        first_piece[b] = static_cast<int64_t>(pieces.size());
+        for (int64_t lo = block_start[b]; lo < block_start[b + 1]; lo += piece_entries)
+            pieces.push_back({b, lo, std::min(block_start[b + 1], lo + piece_entries)});
+    }
+    first_piece[n_blocks] = static_cast<int64_t>(pieces.size());
+    const int64_t n_pieces = static_cast<int64_t>(pieces.size());
+    std::vector<int64_t> piece_pos(static_cast<size_t>(n_pieces) * block_genes);    // [piece][gene of block]: count, then offset
+    std::atomic<long long> next{0};
+    run_threads(threads, [&](int) {
+        for (;;) {
+            const long long k = next.fetch_add(1);
+            if (k >= n_pieces) return;
+            int64_t *cnt = piece_pos.data() + static_cast<size_t>(k) * block_genes;
+            std::fill(cnt, cnt + block_genes, 0);
+            for (const uint32_t *p = packed + pieces[k].lo, *e = packed + pieces[k].hi; p < e; ++p) ++cnt[*p >> 16];
+        }
+    });
+    next.store(0);
+    run_threads(threads, [&](int) {
+        for (;;) {
+            const long long b = next.fetch_add(1);
+            if (b >= n_blocks) return;
+            const int64_t g0 = b << shift, g1 = std::min<int64_t>(n_genes, g0 + block_genes);
+            int64_t at = block_start[b];
+            for (int64_t g = g0; g < g1; ++g) {
+                for (int64_t k = first_piece[b]; k < first_piece[b + 1]; ++k) {
+                    int64_t &slot = piece_pos[static_cast<size_t>(k) * block_genes + (g - g0)];
+                    const int64_t c = slot;
+                    slot = at;
+                    at += c;
+                }
+                indptr[g + 1] = at;            // indptr[g0] belongs to the previous block (indptr[0] = 0)
+            }
+        }
+    });
+    next.store(0);
     std::vector<std::vector<int32_t>> part_colsum(threads);
-    std::atomic<long long> next{0}, dups{0};
     run_threads(threads, [&](int t) {
         std::vector<int32_t> &cs = part_colsum[t];
         cs.assign(n_genomes, 0);
-        std::vector<int64_t> pos(static_cast<size_t>(1) << shift);
-        long long d = 0;
         for (;;) {
-            const long long b = next.fetch_add(1);
-            if (b >= n_blocks) break;
-            const int64_t g0 = b << shift, g1 = std::min<int64_t>(n_genes, g0 + (1ll << shift));
-            const uint32_t *src = packed.get() + block_start[b], *end = packed.get() + block_start[b + 1];
-            std::fill(pos.begin(), pos.end(), 0);
-            for (const uint32_t *p = src; p < end; ++p) ++pos[*p >> 16];
-            int64_t at = block_start[b];
-            for (int64_t g = g0; g < g1; ++g) {
-                const int64_t c = pos[g - g0];
-                pos[g - g0] = at;
-                indptr[g + 1] = at + c;          // indptr[g0] is written by the previous block (or is indptr[0] = 0)
-                at += c;
-            }
-            for (const uint32_t *p = src; p < end; ++p) {
+            const long long k = next.fetch_add(1);
+            if (k >= n_pieces) return;
+            int64_t *pos = piece_pos.data() + static_cast<size_t>(k) * block_genes;
+            for (const uint32_t *p = packed + pieces[k].lo, *e = packed + pieces[k].hi; p < e; ++p) {
                 const uint32_t c = *p & 0xffffu;
                 indices[pos[*p >> 16]++] = static_cast<int32_t>(c);
                 ++cs[c];
             }
-            for (int64_t g = g0; g < g1; ++g) {
-                int32_t *a = indices + (g == g0 ? block_start[b] : indptr[g]), *e = indices + indptr[g + 1];
+        }
+    });
+    for (int t = 0; t < threads; ++t)
+        for (size_t c = 0; c < part_colsum[t].size(); ++c) colsum[c] += part_colsum[t][c];
+
+    // pass C: canonical rows, gene chunks of about 2^18 entries
+    std::vector<int64_t> chunk_first;
+    for (int64_t g = 0; g < n_genes;) {
+        chunk_first.push_back(g);
+        const int64_t limit = indptr[g] + (1ll << 18);
+        ++g;
+        while (g < n_genes && indptr[g + 1] <= limit) ++g;
+    }
+    chunk_first.push_back(n_genes);
+    const int64_t n_chunks = static_cast<int64_t>(chunk_first.size()) - 1;
+    std::atomic<long long> dups{0};
+    next.store(0);
+    run_threads(threads, [&](int) {
+        std::vector<uint64_t> seen((static_cast<size_t>(n_genomes) + 63) / 64, 0);
+        long long d = 0;
+        for (;;) {
+            const long long k = next.fetch_add(1);
+            if (k >= n_chunks) break;
+            for (int64_t g = chunk_first[k]; g < chunk_first[k + 1]; ++g) {
+                int32_t *a = indices + indptr[g], *e = indices + indptr[g + 1];
                 bool sorted = true;
                 for (int32_t *p = a + 1; p < e; ++p) {
                     if (p[0] <= p[-1]) {
@@ -389,16 +475,40 @@ extern "C" int pgx_plan_coo_to_csr(const int32_t *row, const int32_t *col, int64
                         break;
                     }
                 }
-                if (!sorted) {
+                if (sorted) continue;
+                if (static_cast<size_t>(e - a) * 16 < seen.size()) {
                     std::sort(a, e);
                     for (int32_t *p = a + 1; p < e; ++p) d += p[0] == p[-1];
+                    continue;
                 }
+                // long row: mark the genomes in a bitmap, re-emit them ascending; duplicates follow the
+                // distinct genomes (still counted, the caller rejects the table anyway)
+                int32_t *dup_tail = e;
+                for (int32_t *p = a; p < e; ++p) {
+                    const uint32_t c = static_cast<uint32_t>(*p);
+                    if (seen[c >> 6] >> (c & 63) & 1) {
+                        ++d;
+                        --dup_tail;               // remember how many slots the duplicates need
+                    }
+                    seen[c >> 6] |= 1ull << (c & 63);
+                }
+                const long long n_dup = e - dup_tail;
+                int32_t last = 0;
+                int32_t *w = a;
+                for (size_t word = 0; word < seen.size(); ++word) {
+                    uint64_t bits = seen[word];
+                    seen[word] = 0;
+                    while (bits) {
+                        last = static_cast<int32_t>(word * 64 + __builtin_ctzll(bits));
+                        *w++ = last;
+                        bits &= bits - 1;
+                    }
+                }
+                for (long long x = 0; x < n_dup; ++x) *w++ = last;      // keeps nnz; content is void once d > 0
             }
         }
         dups.fetch_add(d);
     });
-    for (int t = 0; t < threads; ++t)
-        for (size_t c = 0; c < part_colsum[t].size(); ++c) colsum[c] += part_colsum[t][c];
     *n_duplicates = dups.load();
     return PGX_OK;
 }
@@ -484,4 +594,20 @@ extern "C" int pgx_plan_missing_genome(const int64_t *indptr, const int32_t *ind
     });
     if (bad.load()) return pgx::fail(PGX_ERR_INVALID, "rows passed to pgx_plan_missing_genome are not single-absence rows");
     return PGX_OK;
+}
+
+// 1 when every 64-bit word of ``words`` equals ``value`` (the planner's "all stored values are 1" test for
+// int64 and float64 tables), else 0.
+extern "C" int pgx_plan_all_equal_u64(const uint64_t *words, int64_t n, uint64_t value, int32_t n_threads)
+{
+    if (n <= 0 || !words) return n <= 0 ? 1 : 0;
+    const int threads = host_threads(n_threads, std::max<long long>(1, n / (1 << 18)));
+    std::atomic<int> differs{0};
+    run_threads(threads, [&](int t) {
+        const int64_t lo = n * t / threads, hi = n * (t + 1) / threads;
+        uint64_t acc = 0;
+        for (int64_t i = lo; i < hi; ++i) acc |= words[i] ^ value;
+        if (acc) differs.store(1);
+    });
+    return differs.load() ? 0 : 1;
 }

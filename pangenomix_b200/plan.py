@@ -190,10 +190,15 @@ def canonical_csr(data):
     """
     if (not _numpy_spec() and scipy.sparse.issparse(data) and data.format == "coo" and data.ndim == 2
             and 0 < data.shape[1] <= MAX_GENOMES and data.shape[0] < 2 ** 31 - 1 and data.nnz > 0):
+        from . import _native
+        import ctypes
         values = np.asarray(data.data)
-        if values.dtype != object and bool(np.all(values == 1)):
-            from . import _native
-            import ctypes
+        if values.dtype in (np.dtype(np.int64), np.dtype(np.float64)) and values.flags.c_contiguous:
+            one = 1 if values.dtype == np.dtype(np.int64) else int(np.float64(1.0).view(np.uint64))
+            all_ones = bool(_native.load().pgx_plan_all_equal_u64(values.ctypes.data, values.shape[0], one, 0))
+        else:
+            all_ones = values.dtype != object and bool(np.all(values == 1))
+        if all_ones:
             n_genes, n = (int(v) for v in data.shape)
             row = np.ascontiguousarray(data.row, dtype=np.int32)
             col = np.ascontiguousarray(data.col, dtype=np.int32)
