@@ -33,12 +33,20 @@
 #include <sys/mman.h>
 #include <unistd.h>
 
+#include <algorithm>
+#include <atomic>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <vector>
 
 #include "pgx_common.cuh"
+
+#ifdef MADV_POPULATE_WRITE
+#define PGX_MADV_POPULATE_WRITE MADV_POPULATE_WRITE
+#else
+#define PGX_MADV_POPULATE_WRITE 23      // Linux >= 5.14; older kernels answer EINVAL and the hint is dropped
+#endif
 
 namespace pgx {
 
@@ -839,6 +847,31 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
         const uintptr_t hi = (reinterpret_cast<uintptr_t>(h_curves) + sizeof(double) * 2ull * n * n_iter) & ~(page - 1);
         if (hi > lo) madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
     }
+    // ... and let a few threads fault its pages in (MADV_POPULATE_WRITE leaves the contents alone) while the
+    // first shuffles are drawn: the staging -> result copies below then run at memcpy speed instead of
+    // page-fault speed.  Chunks are handed out in address order, so the populated frontier stays ahead of
+    // the copies; where it does not, or the kernel lacks the call, the copy simply faults as before.
+    std::vector<std::thread> populators;
+    std::atomic<long long> populate_next{0};
+    {
+        const size_t total = sizeof(double) * 2ull * n * n_iter, chunk = 8u << 20;
+        const int want = total >= (64u << 20) ? std::max(1, std::min(4, static_cast<int>(std::thread::hardware_concurrency()) / 4)) : 0;
+        char *base = reinterpret_cast<char *>(h_curves);
+        for (int t = 0; t < want; ++t)
+            populators.emplace_back([&populate_next, base, total, chunk]() {
+                for (;;) {
+                    const size_t lo = static_cast<size_t>(populate_next.fetch_add(1)) * chunk;
+                    if (lo >= total) return;
+                    const uintptr_t a = (reinterpret_cast<uintptr_t>(base) + lo) & ~uintptr_t(4095);
+                    const uintptr_t b = (reinterpret_cast<uintptr_t>(base) + std::min(total, lo + chunk)) & ~uintptr_t(4095);
+                    if (b > a && madvise(reinterpret_cast<void *>(a), b - a, PGX_MADV_POPULATE_WRITE) != 0) return;
+                }
+            });
+    }
+    struct JoinAll {
+        std::vector<std::thread> &threads;
+        ~JoinAll() { for (auto &t : threads) t.join(); }
+    } join_populators{populators};
 
     // producer -> consumer hand-off: ``issued`` blocks have their GPU work enqueued, ``retired`` blocks
     // have been copied out; slot of block k is k % 3, reusable once block k - 3 retired
