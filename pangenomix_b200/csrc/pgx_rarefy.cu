@@ -33,20 +33,13 @@
 #include <sys/mman.h>
 #include <unistd.h>
 
-#include <algorithm>
-#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <vector>
 
 #include "pgx_common.cuh"
-
-#ifdef MADV_POPULATE_WRITE
-#define PGX_MADV_POPULATE_WRITE MADV_POPULATE_WRITE
-#else
-#define PGX_MADV_POPULATE_WRITE 23      // Linux >= 5.14; older kernels answer EINVAL and the hint is dropped
-#endif
 
 namespace pgx {
 
@@ -847,31 +840,11 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
         const uintptr_t hi = (reinterpret_cast<uintptr_t>(h_curves) + sizeof(double) * 2ull * n * n_iter) & ~(page - 1);
         if (hi > lo) madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
     }
-    // ... and let a few threads fault its pages in (MADV_POPULATE_WRITE leaves the contents alone) while the
-    // first shuffles are drawn: the staging -> result copies below then run at memcpy speed instead of
-    // page-fault speed.  Chunks are handed out in address order, so the populated frontier stays ahead of
-    // the copies; where it does not, or the kernel lacks the call, the copy simply faults as before.
-    std::vector<std::thread> populators;
-    std::atomic<long long> populate_next{0};
-    {
-        const size_t total = sizeof(double) * 2ull * n * n_iter, chunk = 8u << 20;
-        const int want = total >= (64u << 20) ? std::max(1, std::min(4, static_cast<int>(std::thread::hardware_concurrency()) / 4)) : 0;
-        char *base = reinterpret_cast<char *>(h_curves);
-        for (int t = 0; t < want; ++t)
-            populators.emplace_back([&populate_next, base, total, chunk]() {
-                for (;;) {
-                    const size_t lo = static_cast<size_t>(populate_next.fetch_add(1)) * chunk;
-                    if (lo >= total) return;
-                    const uintptr_t a = (reinterpret_cast<uintptr_t>(base) + lo) & ~uintptr_t(4095);
-                    const uintptr_t b = (reinterpret_cast<uintptr_t>(base) + std::min(total, lo + chunk)) & ~uintptr_t(4095);
-                    if (b > a && madvise(reinterpret_cast<void *>(a), b - a, PGX_MADV_POPULATE_WRITE) != 0) return;
-                }
-            });
-    }
-    struct JoinAll {
-        std::vector<std::thread> &threads;
-        ~JoinAll() { for (auto &t : threads) t.join(); }
-    } join_populators{populators};
+
+    // PGX_ESTIMATE_TRACE=1: per-block timeline of the pipeline on stderr (development aid)
+    const bool trace = getenv("PGX_ESTIMATE_TRACE") != nullptr;
+    const auto trace_t0 = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - trace_t0).count(); };
 
     // producer -> consumer hand-off: ``issued`` blocks have their GPU work enqueued, ``retired`` blocks
     // have been copied out; slot of block k is k % 3, reusable once block k - 3 retired
@@ -889,13 +862,16 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
             }
             pgx::EstimateSlot &s = buf.slot[k % 3];
             const long long p0 = k * block, cnt = std::min<long long>(block, n_iter - p0);
+            const double t_wait = since();
             int rc = pgx_legacy_shuffles(mt_key, mt_pos, n, cnt, s.h_perm);
+            const double t_rng = since();
             if (!rc && cudaMemcpyAsync(s.d_perm, s.h_perm, sizeof(uint16_t) * cnt * n, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
                 rc = pgx::fail(PGX_ERR_CUDA, "H2D copy of the permutations failed");
             if (!rc) rc = pgx::run_curves<double>(plan, s.d_perm, cnt, s.d_hist, s.d_out, s.stream, &s.aux);
             if (!rc && cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * cnt * 2 * n, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
                 rc = pgx::fail(PGX_ERR_CUDA, "D2H copy of the curves failed");
             if (!rc && cudaEventRecord(s.done, s.stream) != cudaSuccess) rc = pgx::fail(PGX_ERR_CUDA, "event record failed");
+            if (trace) fprintf(stderr, "[pgx trace] block %lld: rng %.2f -> %.2f ms, enqueued %.2f ms\n", k, t_wait, t_rng, since());
             {
                 std::lock_guard<std::mutex> lk(mu);
                 if (rc) {
@@ -925,6 +901,7 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
             cv.notify_all();
             break;
         }
+        const double t_ready = since();
         {
             // staging -> result with a few threads: one core fills fresh pages at only ~8 GB/s
             const size_t bytes = sizeof(double) * cnt * 2 * n;
@@ -944,6 +921,7 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
             retired = k + 1;
         }
         cv.notify_all();
+        if (trace) fprintf(stderr, "[pgx trace] block %lld: on the host %.2f ms, copied out %.2f ms\n", k, t_ready, since());
     }
     {
         std::lock_guard<std::mutex> lk(mu);

@@ -398,10 +398,14 @@ extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n,
         }
     } else {
         // producer (this thread): stages 1-2 into a ring of batch buffers; workers: stage 3
-        struct Slot { std::vector<uint32_t> js; int64_t first = 0; int count = 0; };
+        // The ring's buffers outlive the call (guarded by call_mu): a caller that draws block after block
+        // (pgx_estimate_pan_core) would otherwise pay for zero-filling ~5 MB of fresh pages per call.
+        struct Slot { uint32_t *js = nullptr; int64_t first = 0; int count = 0; };
         const int n_slots = 2 * workers + 2;
+        static std::vector<uint32_t> ring;
+        if (ring.size() < stride * batch * n_slots) ring.resize(stride * batch * n_slots);
         std::vector<Slot> slots(n_slots);
-        for (auto &s : slots) s.js.resize(stride * batch);
+        for (int s = 0; s < n_slots; ++s) slots[s].js = ring.data() + stride * batch * s;
         std::mutex mu;
         std::condition_variable cv_work, cv_free;
         std::deque<int> ready, free_slots;
@@ -419,7 +423,7 @@ extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n,
                         s = ready.front();
                         ready.pop_front();
                     }
-                    apply_batch(un, stride, slots[s].js.data(), h_perms + slots[s].first * n, slots[s].count);
+                    apply_batch(un, stride, slots[s].js, h_perms + slots[s].first * n, slots[s].count);
                     {
                         std::lock_guard<std::mutex> lock(mu);
                         free_slots.push_back(s);
@@ -437,7 +441,7 @@ extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n,
                 free_slots.pop_front();
             }
             const int c = static_cast<int>(std::min<int64_t>(batch, count - t));
-            for (int b = 0; b < c; ++b) accept_one(mt, un, slots[s].js.data() + b * stride);
+            for (int b = 0; b < c; ++b) accept_one(mt, un, slots[s].js + b * stride);
             slots[s].first = t;
             slots[s].count = c;
             {
