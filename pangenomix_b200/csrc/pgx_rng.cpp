@@ -251,18 +251,49 @@ void accept_avx512_span(Mt19937 &mt, uint32_t &i_io, uint32_t lo, uint32_t mask,
     uint32_t *w = w_io;
     int pos = mt.pos;
     const __m512i maskv = _mm512_set1_epi32(static_cast<int>(mask));
-    // 16 draws per vector: lane l is tested against i - (accepts among lanes < l), in [i - 15, i]
+    // A draw is tested against i - (accepts before it in the step).  For the 16 draws of a vector that
+    // lies in [i - 15, i]: v <= i - 15 is a sure accept, v > i a sure reject, and the few lanes in
+    // between are settled one by one, in order, from the accepts before them.  While at least 32 accepts
+    // remain under this mask, two vectors go through per step if none of their lanes is in doubt for the
+    // window [i - 31, i]: the loop-carried chain (i -> compares -> popcount -> i) is paid once per 32 draws.
     while (i >= lo + 16) {
         if (pos + 16 > 624) {
             if (pos >= 624) { mt.refill(); pos = 0; continue; }
             break;                                   // block tail: the scalar loop finishes it
         }
-        const __m512i v = _mm512_and_si512(_mm512_loadu_si512(mt.out + pos), maskv);
-        const __mmask16 sure = _mm512_cmple_epu32_mask(v, _mm512_set1_epi32(static_cast<int>(i - 15)));
-        const __mmask16 over = _mm512_cmpgt_epu32_mask(v, _mm512_set1_epi32(static_cast<int>(i)));
-        if (static_cast<unsigned>(sure | over) != 0xffffu) break;    // an ambiguous lane: resolve this vector one by one
-        _mm512_storeu_si512(w, _mm512_maskz_compress_epi32(sure, v));
-        const uint32_t got = static_cast<uint32_t>(_mm_popcnt_u32(static_cast<unsigned>(sure)));
+        const __m512i v0 = _mm512_and_si512(_mm512_loadu_si512(mt.out + pos), maskv);
+        const __m512i top_v = _mm512_set1_epi32(static_cast<int>(i));
+        const __mmask16 over0 = _mm512_cmpgt_epu32_mask(v0, top_v);
+        if (i >= lo + 32 && pos + 32 <= 624) {
+            const __m512i v1 = _mm512_and_si512(_mm512_loadu_si512(mt.out + pos + 16), maskv);
+            const __m512i floor_v = _mm512_set1_epi32(static_cast<int>(i - 31));
+            const __mmask16 sure0 = _mm512_cmple_epu32_mask(v0, floor_v), sure1 = _mm512_cmple_epu32_mask(v1, floor_v);
+            const __mmask16 over1 = _mm512_cmpgt_epu32_mask(v1, top_v);
+            if (static_cast<unsigned>((sure0 | over0) & (sure1 | over1)) == 0xffffu) {
+                const uint32_t got0 = static_cast<uint32_t>(_mm_popcnt_u32(static_cast<unsigned>(sure0)));
+                const uint32_t got1 = static_cast<uint32_t>(_mm_popcnt_u32(static_cast<unsigned>(sure1)));
+                _mm512_storeu_si512(w, _mm512_maskz_compress_epi32(sure0, v0));
+                _mm512_storeu_si512(w + got0, _mm512_maskz_compress_epi32(sure1, v1));
+                w += got0 + got1;
+                i -= got0 + got1;
+                pos += 32;
+                continue;
+            }
+        }
+        unsigned acc = _mm512_cmple_epu32_mask(v0, _mm512_set1_epi32(static_cast<int>(i - 15)));
+        unsigned doubt = ~(acc | over0) & 0xffffu;
+        if (doubt) {
+            alignas(64) uint32_t lanes[16];
+            _mm512_store_si512(lanes, v0);
+            do {
+                const int l = __builtin_ctz(doubt);
+                doubt &= doubt - 1;
+                const uint32_t before = static_cast<uint32_t>(_mm_popcnt_u32(acc & ((1u << l) - 1u)));
+                if (lanes[l] <= i - before) acc |= 1u << l;
+            } while (doubt);
+        }
+        _mm512_storeu_si512(w, _mm512_maskz_compress_epi32(static_cast<__mmask16>(acc), v0));
+        const uint32_t got = static_cast<uint32_t>(_mm_popcnt_u32(acc));
         w += got;
         i -= got;
         pos += 16;
