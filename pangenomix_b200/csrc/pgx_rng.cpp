@@ -42,8 +42,10 @@ constexpr uint32_t MT_UPPER = 0x80000000u, MT_LOWER = 0x7fffffffu, MT_MAGIC = 0x
 // exactly as np.random.get_state() reports it.
 struct Mt19937 {
     alignas(64) uint32_t key[624 + 8];
-    alignas(64) uint32_t out[624 + 8];
-    int pos;
+    alignas(64) uint32_t prev_key[624 + 8];        // key of the block the carried words came from (carry_tail)
+    alignas(64) uint32_t out_store[16 + 624 + 8];
+    uint32_t *const out = out_store + 16;           // 64-byte aligned; out[-16 .. 0) holds a carried block tail
+    int pos;                                        // next word: 0 .. 624, or negative while carried words remain
     bool avx2;
     bool avx512 = false;
 
@@ -154,6 +156,20 @@ struct Mt19937 {
     }
 #endif
 
+    // The last 624 - pos (< 16) words of the block move in front of the next block, so that vector loads
+    // run across the block boundary; the old key is kept in case the call ends inside the carried words
+    // (the numpy state to report is then {prev_key, 624 - remaining}).
+    void carry_tail()
+    {
+        const int rem = 624 - pos;
+        uint32_t tail[16];
+        memcpy(tail, out + pos, sizeof(uint32_t) * rem);
+        memcpy(prev_key, key, sizeof(uint32_t) * 624);
+        refill();
+        memcpy(out - rem, tail, sizeof(uint32_t) * rem);
+        pos = -rem;
+    }
+
     void refill()
     {
 #if PGX_X86
@@ -258,8 +274,10 @@ void accept_avx512_span(Mt19937 &mt, uint32_t &i_io, uint32_t lo, uint32_t mask,
     // window [i - 31, i]: the loop-carried chain (i -> compares -> popcount -> i) is paid once per 32 draws.
     while (i >= lo + 16) {
         if (pos + 16 > 624) {
-            if (pos >= 624) { mt.refill(); pos = 0; continue; }
-            break;                                   // block tail: the scalar loop finishes it
+            mt.pos = pos;
+            if (pos >= 624) mt.refill(); else mt.carry_tail();
+            pos = mt.pos;
+            continue;
         }
         const __m512i v0 = _mm512_and_si512(_mm512_loadu_si512(mt.out + pos), maskv);
         const __m512i top_v = _mm512_set1_epi32(static_cast<int>(i));
@@ -488,7 +506,12 @@ extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n,
         cv_work.notify_all();
         for (auto &th : pool) th.join();
     }
-    memcpy(mt_key, mt.key, sizeof(uint32_t) * 624);
-    *mt_pos = mt.pos;
+    if (mt.pos < 0) {                              // the call ended inside a carried block tail
+        memcpy(mt_key, mt.prev_key, sizeof(uint32_t) * 624);
+        *mt_pos = 624 + mt.pos;
+    } else {
+        memcpy(mt_key, mt.key, sizeof(uint32_t) * 624);
+        *mt_pos = mt.pos;
+    }
     return PGX_OK;
 }

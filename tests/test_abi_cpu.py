@@ -88,6 +88,29 @@ def test_legacy_shuffles_vector_and_threaded_paths(monkeypatch, n, count, mode):
     assert np.array_equal(after[1], ref_after[1]) and after[2] == ref_after[2]
 
 
+@pytest.mark.parametrize("n", [33, 1000, 10000])
+def test_legacy_shuffles_calls_interleaved_with_numpy_draws(n):
+    """Many short calls, numpy's own draws between them: calls end at every position of an MT19937 block,
+    also inside a block tail that the AVX-512 span has carried in front of the next block (the exported
+    state is then the previous block's key), and the state handed back must be numpy's every time."""
+    sizes = [1 + (7 * k) % 5 for k in range(max(12, 120000 // n))]
+    np.random.seed(31)
+    got = []
+    for c in sizes:
+        got.append(engine.draw_legacy_permutations(n, c))
+        np.random.random_sample(3)
+    state = np.random.get_state()
+    np.random.seed(31)
+    for c, block in zip(sizes, got):
+        for row in block:
+            a = np.arange(n)
+            np.random.shuffle(a)
+            assert np.array_equal(a, row)
+        np.random.random_sample(3)
+    ref = np.random.get_state()
+    assert np.array_equal(state[1], ref[1]) and state[2] == ref[2]
+
+
 def test_legacy_shuffles_mid_block_state_and_numpy_mode(monkeypatch):
     np.random.seed(99)
     np.random.random_sample(123)           # leave the generator mid-block
