@@ -41,6 +41,23 @@ def _engine_for(df_genes, device=None):
     return engine
 
 
+_LABEL_CACHE = {}
+
+
+def _labels(prefixes, count):
+    """pd.Index of prefix1..prefixN for every prefix in turn, exactly what pandas makes of the reference's label
+    lists (pangenome_analysis.py:93-97).  The label data is immutable, so it is shared between calls: building
+    the 20,000 column labels of a 10,000-genome table costs more than rarefying 500 permutations."""
+    key = (prefixes, int(count))
+    index = _LABEL_CACHE.get(key)
+    if index is None:
+        if len(_LABEL_CACHE) >= 16:
+            _LABEL_CACHE.pop(next(iter(_LABEL_CACHE)))
+        index = pd.Index([prefix + str(x) for prefix in prefixes for x in range(1, int(count) + 1)])
+        _LABEL_CACHE[key] = index
+    return index.copy(deep=False)          # a new Index object over the shared labels (its .name stays private)
+
+
 def fit_heaps_by_iteration(df_pan_core):
     '''
     Fits Heaps Law (PG size = kappa * genomes^alpha) to the Pan half of every row of a
@@ -110,11 +127,10 @@ def estimate_pan_core_size(df_genes, num_iter, log_batch=-1, device=None):
     print('Generating pan/core curves from shuffled strains')
     curves = engine.estimate(num_iter, log_batch=log_batch)
 
-    iter_index = ['Iter' + str(x) for x in range(1, num_iter + 1)]
-    pan_cols = ['Pan' + str(x) for x in range(1, num_strains + 1)]
-    core_cols = ['Core' + str(x) for x in range(1, num_strains + 1)]
-    # the curves are a fresh array nobody else holds: wrap it instead of copying it (pandas 3 copies by default)
-    return pd.DataFrame(curves, index=iter_index, columns=pan_cols + core_cols, copy=False)
+    # labels of :93-95; the curves are a fresh array nobody else holds: wrap it instead of copying it
+    # (pandas 3 copies by default)
+    return pd.DataFrame(curves, index=_labels(('Iter',), num_iter),
+                        columns=_labels(('Pan', 'Core'), num_strains), copy=False)
 
 
 def compute_bernoulli_grid_core_genome(df_genes_dense,
