@@ -909,7 +909,7 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
             const size_t bytes = sizeof(double) * cnt * 2 * n;
             char *dst = reinterpret_cast<char *>(h_curves + p0 * 2 * n);
             const char *src = reinterpret_cast<const char *>(s.h_out);
-            const int parts = bytes >= (8u << 20) ? copy_threads : 1;
+            const int parts = static_cast<int>(std::max<size_t>(1, std::min<size_t>(copy_threads, bytes >> 20)));   // >= 1 MB each
             std::vector<std::thread> movers;
             for (int t = 1; t < parts; ++t) {
                 const size_t lo = bytes / parts * t, hi = t + 1 == parts ? bytes : bytes / parts * (t + 1);
