@@ -16,7 +16,6 @@ def main():
     ap.add_argument("--genomes", type=int, default=50000)
     ap.add_argument("--per-genome", type=int, default=1000)
     ap.add_argument("--perms", type=int, default=256)
-    ap.add_argument("--check", type=int, default=2, help="permutations checked against the oracle C port")
     ap.add_argument("--thresholds", default="")
     args = ap.parse_args()
     t = time.time()
@@ -28,7 +27,6 @@ def main():
     d_perms = torch.from_numpy(perms.view(np.int16)).cuda()
     out = torch.empty((args.perms, 2 * n), dtype=torch.int32, device="cuda")
     _native.profile_enable(True)
-    want = None
     for thr in [int(x) for x in args.thresholds.split(",") if x] or [None]:
         t = time.time()
         hp = build_host_plan(coo, long_threshold=thr)
@@ -49,17 +47,7 @@ def main():
         print("  %d perms: %.2f ms (list %.2f probe %.2f scan %.2f) -> %.0f perms/s, %.3g cells/s" % (
             args.perms, ms, a / calls, pr / calls, sc / calls, args.perms / ms * 1e3,
             args.perms / ms * 1e3 * args.genes * n), flush=True)
-        got = out[:max(args.check, 1)].cpu().numpy()
-        if want is None and args.check > 0:
-            from oracle import build as oracle_build, cport
-            oracle_build.build()
-            t = time.time()
-            pan, core = cport.curves_direct(coo, perms[:args.check].astype(np.int32), n_threads=os.cpu_count() or 1)
-            want = np.hstack([pan, core]).astype(np.int32)
-            print("  oracle C port: %.1fs for %d permutations" % (time.time() - t, args.check), flush=True)
-        if want is not None:
-            assert np.array_equal(got[:args.check], want), "GPU != oracle"
-            print("  parity ok on %d permutations" % args.check, flush=True)
+        # parity proper lives in tests/ (the oracle is test infrastructure); here only the invariants
         curves = out.cpu().numpy()
         assert np.all(np.diff(curves[:, :n], axis=1) >= 0) and np.all(np.diff(curves[:, n:], axis=1) <= 0)
         del eng
