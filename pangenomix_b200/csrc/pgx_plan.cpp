@@ -38,10 +38,15 @@ struct Group {
 };
 
 // plan._colour_groups for one group: greedy edge colouring of lanes x residues with n_steps colours.
+// Same choices as the numpy specification (first maximum wins, stable order of the lanes), found with
+// less work: the residues a lane still holds are a bit mask, so a lane scans only those; the lane order
+// by slack is kept between steps (a lane's slack changes by at most one per step) and repaired by an
+// insertion sort on the unique keys slack * 32 + lane.
 void colour(Group &g)
 {
     const int R = g.r_mod, S = g.n_steps;
-    int cnt[MAX_MOD][MAX_MOD], colload[MAX_MOD], rem[MAX_MOD];
+    int cnt[MAX_MOD][MAX_MOD], colload[MAX_MOD], rem[MAX_MOD], order[MAX_MOD];
+    uint32_t holds[MAX_MOD];                           // bit r: the lane still has entries of residue r
     memcpy(cnt, g.cnt, sizeof(cnt));
     for (int r = 0; r < R; ++r) {
         colload[r] = 0;
@@ -49,52 +54,62 @@ void colour(Group &g)
     }
     for (int l = 0; l < R; ++l) {
         rem[l] = 0;
-        for (int r = 0; r < R; ++r) rem[l] += cnt[l][r];
+        holds[l] = 0;
+        order[l] = l;
+        for (int r = 0; r < R; ++r) {
+            rem[l] += cnt[l][r];
+            if (cnt[l][r] > 0) holds[l] |= 1u << r;
+        }
     }
     for (int s = 0; s < S; ++s) {
-        bool taken[MAX_MOD] = {false};
+        uint32_t taken = 0;
         const int steps_left = S - s;
-        // rows with the least slack choose first (stable argsort of steps_left - rem)
-        int order[MAX_MOD];
-        for (int l = 0; l < R; ++l) order[l] = l;
-        std::stable_sort(order, order + R, [&](int a, int b) { return steps_left - rem[a] < steps_left - rem[b]; });
+        // rows with the least slack choose first: ascending (steps_left - rem, lane), i.e. descending rem, then lane
+        for (int a = 1; a < R; ++a) {
+            const int lane = order[a];
+            int at = a;
+            while (at > 0 && (rem[order[at - 1]] < rem[lane] || (rem[order[at - 1]] == rem[lane] && order[at - 1] > lane))) {
+                order[at] = order[at - 1];
+                --at;
+            }
+            order[at] = lane;
+        }
         for (int t = 0; t < R; ++t) {
             const int lane = order[t];
-            int choice = 0;
-            long best = -2;
-            bool has = false;
-            for (int r = 0; r < R; ++r) {              // argmax of colload * 1024 + cnt over available residues (first max wins)
-                const bool avail = cnt[lane][r] > 0 && !taken[r];
-                const long score = avail ? static_cast<long>(colload[r]) * 1024 + cnt[lane][r] : -1;
+            int choice = -1;
+            long best = -1;
+            for (uint32_t m = holds[lane] & ~taken; m; m &= m - 1) {   // argmax of colload * 1024 + cnt, first max wins
+                const int r = __builtin_ctz(m);
+                const long score = static_cast<long>(colload[r]) * 1024 + cnt[lane][r];
                 if (score > best) {
                     best = score;
                     choice = r;
-                    has = avail;
                 }
             }
-            const bool forced = !has && rem[lane] >= steps_left && rem[lane] > 0;
-            if (forced) {
+            if (choice < 0 && rem[lane] >= steps_left && rem[lane] > 0) {   // forced: no free residue, no slack left
                 int top = -1;
-                for (int r = 0; r < R; ++r)
+                for (uint32_t m = holds[lane]; m; m &= m - 1) {
+                    const int r = __builtin_ctz(m);
                     if (cnt[lane][r] > top) {
                         top = cnt[lane][r];
                         choice = r;
                     }
+                }
             }
-            if (has || forced) {
+            if (choice >= 0) {
                 g.res_at[lane * S + s] = static_cast<int8_t>(choice);
-                --cnt[lane][choice];
+                if (--cnt[lane][choice] == 0) holds[lane] &= ~(1u << choice);
                 --colload[choice];
                 --rem[lane];
-                taken[choice] = true;
+                taken |= 1u << choice;
             }
         }
         // pads: the k-th idle lane of the group takes the group's k-th unused residue
         int free_order[MAX_MOD], n_free = 0;
         for (int r = 0; r < R; ++r)
-            if (!taken[r]) free_order[n_free++] = r;
+            if (!(taken >> r & 1)) free_order[n_free++] = r;
         for (int r = 0; r < R; ++r)
-            if (taken[r]) free_order[n_free++] = r;
+            if (taken >> r & 1) free_order[n_free++] = r;
         int rank = 0;
         for (int l = 0; l < R; ++l) {
             if (g.res_at[l * S + s] < 0) {
