@@ -446,6 +446,95 @@ scan_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const int32
     }
 }
 
+// EXPERIMENT, off unless PGX_SCAN_V8=1 (not yet measured or parity-checked on a GPU): the same scan with
+// 16-byte loads and stores, 8 bins per thread, for tables whose genome count is a multiple of 8.
+template <typename OutT>
+__global__ void __launch_bounds__(256)
+scan_kernel_v8(const pgx_plan plan, const uint16_t *__restrict__ perms, const int32_t *hist, OutT *out)
+{
+    constexpr int ITEMS = 8;
+    constexpr int THREADS = 256;
+    __shared__ int warp_tot[THREADS / 32];
+
+    const int n = plan.n_genomes;                    // n % 8 == 0 (checked by the launcher)
+    const long long p = blockIdx.x;
+    const int side = blockIdx.y;
+    const int32_t *h = hist + p * 2ll * n + static_cast<long long>(side) * n;
+    OutT *o = out + p * 2ll * n + static_cast<long long>(side) * n;
+    const uint16_t *perm = perms + p * n;
+    const int32_t *w_list = side == 0 ? plan.d_w_present : plan.d_w_absent;
+    const int32_t *w_other = side == 0 ? plan.d_w_absent : plan.d_w_present;
+    const int first = perm[0];
+    const int col_first = plan.d_colsum[first];
+    const int bin0 = side == 0 ? col_first : plan.n_genes - col_first;
+    const int add1 = w_other[first];
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int carry = 0;
+    for (int base = 0; base < n; base += THREADS * ITEMS) {
+        const int k0 = base + tid * ITEMS;
+        int v[ITEMS];
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) v[i] = 0;
+        if (k0 < n) {
+            const int4 a = *reinterpret_cast<const int4 *>(h + k0);
+            const int4 b = *reinterpret_cast<const int4 *>(h + k0 + 4);
+            const uint4 pr = *reinterpret_cast<const uint4 *>(perm + k0);
+            v[0] = a.x + w_list[pr.x & 0xffffu];
+            v[1] = a.y + w_list[pr.x >> 16];
+            v[2] = a.z + w_list[pr.y & 0xffffu];
+            v[3] = a.w + w_list[pr.y >> 16];
+            v[4] = b.x + w_list[pr.z & 0xffffu];
+            v[5] = b.y + w_list[pr.z >> 16];
+            v[6] = b.z + w_list[pr.w & 0xffffu];
+            v[7] = b.w + w_list[pr.w >> 16];
+            if (k0 == 0) {
+                v[0] = bin0;
+                v[1] += add1;
+            }
+        }
+        int run = 0;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            run += v[i];
+            v[i] = run;
+        }
+        int incl = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(FULL_MASK, incl, off);
+            if (lane >= off) incl += y;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();
+        int before = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < THREADS / 32; ++i) {
+            const int wt = warp_tot[i];
+            if (i < warp) before += wt;
+            total += wt;
+        }
+        const int excl = carry + before + incl - run;
+        if (k0 < n) {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) {
+                const int c = excl + v[i];
+                v[i] = side == 0 ? c : plan.n_genes - c;
+            }
+            if constexpr (sizeof(OutT) == 4) {
+                *reinterpret_cast<int4 *>(o + k0) = make_int4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<int4 *>(o + k0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
+            } else {
+#pragma unroll
+                for (int i = 0; i < ITEMS; i += 2)
+                    *reinterpret_cast<double2 *>(o + k0 + i) = make_double2(static_cast<double>(v[i]), static_cast<double>(v[i + 1]));
+            }
+        }
+        carry += total;
+        __syncthreads();
+    }
+}
+
 int check_plan(const pgx_plan *plan)
 {
     if (!plan) return fail(PGX_ERR_INVALID, "plan is null");
@@ -625,8 +714,13 @@ int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, 
     for (long long p0 = 0; p0 < n_perm; p0 += 2147483647ll) {
         const long long np = min(2147483647ll, n_perm - p0);
         dim3 grid(static_cast<unsigned>(np), 2);
-        scan_kernel<OutT><<<grid, 256, 0, stream>>>(*plan, d_perms + p0 * n, d_hist + p0 * 2ll * n,
-                                                    d_out + p0 * 2ll * n);
+        static const bool scan_v8 = getenv("PGX_SCAN_V8") != nullptr;       // experiment, see scan_kernel_v8
+        if (scan_v8 && n % 8 == 0)
+            scan_kernel_v8<OutT><<<grid, 256, 0, stream>>>(*plan, d_perms + p0 * n, d_hist + p0 * 2ll * n,
+                                                           d_out + p0 * 2ll * n);
+        else
+            scan_kernel<OutT><<<grid, 256, 0, stream>>>(*plan, d_perms + p0 * n, d_hist + p0 * 2ll * n,
+                                                        d_out + p0 * 2ll * n);
         PGX_LAUNCH_CHECK("scan_kernel");
     }
     if (profile) {
