@@ -202,6 +202,15 @@ int pgx_plan_folded_lists(const int64_t *indptr, const int32_t *indices, const i
                           int32_t *flat, int32_t n_threads);
 int pgx_plan_missing_genome(const int64_t *indptr, const int32_t *indices, const int64_t *genes, int64_t n_rows,
                             int32_t n_genomes, int32_t *missing, int32_t n_threads);
+/* Host-side helper of the planner: the order of the list rows inside their classes (rows of one chunk count and
+ * list kind, consecutive in genes / use_abs / class_key) that balances, per group of ``modulus`` consecutive rows,
+ * how many entries fall on each shared-memory bank residue (genome index modulo ``modulus``): such a group needs at
+ * least max-over-residues(entries of the residue) gather steps however pgx_plan_bank_order arranges them.
+ * order[i] (int64 [n_rows]) = current position of the row that takes place i.  Deterministic; ``window`` = candidates
+ * looked at per choice (pangenomix_b200/plan.py, _balanced_row_order, is the numpy specification). */
+int pgx_plan_balance_rows(const int64_t *indptr, const int32_t *indices, const int64_t *genes,
+                          const uint8_t *use_abs, const int64_t *class_key, int64_t n_rows, int32_t n_genomes,
+                          int32_t modulus, int32_t window, int64_t *order, int32_t n_threads);
 /* Returns 1 when every 64-bit word of words[0 .. n) equals ``value``, else 0: the planner's "every stored value
  * is 1" test for the int64 (value 1) and float64 (value = bits of 1.0) ``data`` arrays of a table. */
 int pgx_plan_all_equal_u64(const uint64_t *words, int64_t n, uint64_t value, int32_t n_threads);

@@ -19,7 +19,7 @@ EXPORTS = (
     "pgx_legacy_shuffles", "pgx_profile_enable", "pgx_profile_read",
     "pgx_heaps_scratch_bytes", "pgx_heaps_fit", "pgx_estimate_pan_core",
     "pgx_plan_bank_order", "pgx_plan_build_bitmap", "pgx_plan_coo_to_csr", "pgx_plan_folded_lists",
-    "pgx_plan_missing_genome", "pgx_plan_all_equal_u64",
+    "pgx_plan_missing_genome", "pgx_plan_all_equal_u64", "pgx_plan_balance_rows",
 )
 
 
@@ -96,6 +96,8 @@ def load():
     lib.pgx_plan_folded_lists.argtypes = [vp, vp, vp, vp, vp, i64, i32, vp, i32]
     lib.pgx_plan_missing_genome.restype = ctypes.c_int
     lib.pgx_plan_missing_genome.argtypes = [vp, vp, vp, i64, i32, vp, i32]
+    lib.pgx_plan_balance_rows.restype = ctypes.c_int
+    lib.pgx_plan_balance_rows.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, i32]
     lib.pgx_plan_all_equal_u64.restype = ctypes.c_int
     lib.pgx_plan_all_equal_u64.argtypes = [vp, i64, ctypes.c_uint64, i32]
     lib.pgx_estimate_pan_core.restype = ctypes.c_int

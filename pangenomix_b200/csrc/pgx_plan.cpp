@@ -7,6 +7,7 @@
 // same greedy edge colouring, same tie breaks, bit-identical output -- as plain loops over the
 // sub-blocks, spread over host threads.  It is O(slots) and removes three quarters of the planning
 // time of large tables.  Nothing here touches the GPU.
+#include <limits.h>
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
@@ -625,4 +626,100 @@ extern "C" int pgx_plan_all_equal_u64(const uint64_t *words, int64_t n, uint64_t
         if (acc) differs.store(1);
     });
     return differs.load() ? 0 : 1;
+}
+
+// plan._balanced_row_order: which list rows share a shared-memory wavefront group.  The lanes of a group
+// (``modulus`` consecutive rows of a sub-block) gather in lock step, one entry each, and two entries collide
+// when their genome indices agree modulo ``modulus``: a group needs at least max over residues of (entries of
+// that residue in the group) steps, however well pgx_plan_bank_order arranges them.  Rows may be put in any
+// order inside a class (same chunk count and list kind), so the groups are formed greedily: the candidates
+// are the class riffled into ``modulus`` parts (neighbours then differ in length), a group starts with the
+// first candidate and then takes, ``modulus`` - 1 times, the candidate among the next ``window`` that keeps
+// the largest residue load of the group smallest (first such candidate wins).
+//   genes / use_abs / class_key : the list rows in their current order; rows of one class are consecutive
+//   order                       : out, int64 [n_rows]: position (in the current order) of the row that goes
+//                                 to each place of the new order
+extern "C" int pgx_plan_balance_rows(const int64_t *indptr, const int32_t *indices, const int64_t *genes,
+                                     const uint8_t *use_abs, const int64_t *class_key, int64_t n_rows,
+                                     int32_t n_genomes, int32_t modulus, int32_t window, int64_t *order,
+                                     int32_t n_threads)
+{
+    if (n_rows < 0 || n_genomes < 1 || window < 1) return pgx::fail(PGX_ERR_INVALID, "bad shape passed to pgx_plan_balance_rows");
+    if (modulus != 8 && modulus != 16 && modulus != 32) return pgx::fail(PGX_ERR_INVALID, "modulus must be 8, 16 or 32");
+    if (n_rows == 0) return PGX_OK;
+    if (!indptr || !indices || !genes || !use_abs || !class_key || !order)
+        return pgx::fail(PGX_ERR_INVALID, "null pointer passed to pgx_plan_balance_rows");
+    const int R = modulus;
+    // residue histogram of every row's folded list
+    std::vector<int32_t> hist(static_cast<size_t>(n_rows) * R);
+    int32_t all[MAX_MOD];
+    for (int r = 0; r < R; ++r) all[r] = (n_genomes - r + R - 1) / R;          // genomes c < N with c % R == r
+    {
+        const long long grain = 1024;
+        std::atomic<long long> next{0};
+        const int threads = host_threads(n_threads, (n_rows + grain - 1) / grain);
+        run_threads(threads, [&](int) {
+            for (;;) {
+                const long long r0 = next.fetch_add(grain);
+                if (r0 >= n_rows) return;
+                const long long r1 = std::min<long long>(n_rows, r0 + grain);
+                for (long long row = r0; row < r1; ++row) {
+                    int32_t *h = hist.data() + static_cast<size_t>(row) * R;
+                    for (int r = 0; r < R; ++r) h[r] = 0;
+                    for (int64_t e = indptr[genes[row]]; e < indptr[genes[row] + 1]; ++e) ++h[indices[e] % R];
+                    if (use_abs[row])
+                        for (int r = 0; r < R; ++r) h[r] = all[r] - h[r];
+                }
+            }
+        });
+    }
+    // classes
+    std::vector<int64_t> class_start;
+    for (int64_t row = 0; row < n_rows; ++row)
+        if (row == 0 || class_key[row] != class_key[row - 1]) class_start.push_back(row);
+    class_start.push_back(n_rows);
+    const long long n_classes = static_cast<long long>(class_start.size()) - 1;
+    std::atomic<long long> next{0};
+    const int threads = host_threads(n_threads, n_classes);
+    run_threads(threads, [&](int) {
+        std::vector<int64_t> seq, cand;
+        for (;;) {
+            const long long k = next.fetch_add(1);
+            if (k >= n_classes) return;
+            const int64_t r0 = class_start[k], cnt = class_start[k + 1] - r0;
+            const int64_t per = (cnt + R - 1) / R;
+            seq.clear();
+            for (int64_t j = 0; j < per; ++j)
+                for (int p = 0; p < R; ++p)
+                    if (j + per * p < cnt) seq.push_back(r0 + j + per * p);
+            int64_t pos = 0, out = r0;
+            cand.clear();
+            while (static_cast<int64_t>(cand.size()) < window && pos < cnt) cand.push_back(seq[pos++]);
+            while (!cand.empty()) {
+                int32_t load[MAX_MOD] = {0};
+                for (int slot = 0; slot < R && !cand.empty(); ++slot) {
+                    size_t pick = 0;
+                    if (slot > 0) {
+                        int32_t best = INT32_MAX;
+                        for (size_t c = 0; c < cand.size(); ++c) {
+                            const int32_t *h = hist.data() + static_cast<size_t>(cand[c]) * R;
+                            int32_t top = 0;
+                            for (int r = 0; r < R; ++r) top = std::max(top, load[r] + h[r]);
+                            if (top < best) {
+                                best = top;
+                                pick = c;
+                            }
+                        }
+                    }
+                    const int64_t row = cand[pick];
+                    cand.erase(cand.begin() + static_cast<long>(pick));
+                    order[out++] = row;
+                    const int32_t *h = hist.data() + static_cast<size_t>(row) * R;
+                    for (int r = 0; r < R; ++r) load[r] += h[r];
+                    if (pos < cnt) cand.push_back(seq[pos++]);
+                }
+            }
+        }
+    });
+    return PGX_OK;
 }

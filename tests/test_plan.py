@@ -226,3 +226,35 @@ def test_plan_native_ingest_errors_and_corner_cases():
     assert lib.pgx_plan_missing_genome(ip.ctypes.data, ix.ctypes.data, genes.ctypes.data, 1, 3, miss.ctypes.data, 1) == 0
     assert miss[0] == 1
     assert lib.pgx_plan_missing_genome(ip.ctypes.data, ix.ctypes.data, genes.ctypes.data, 2, 3, miss.ctypes.data, 1) != 0
+
+
+def test_plan_row_balance_lowers_bank_conflicts(monkeypatch):
+    """Rows are grouped so that the bank residues of a wavefront group are balanced (_balanced_row_order):
+    same rows, same curves, fewer shared-memory wavefronts per gather step than with rows sorted by length;
+    the C++ helper and the numpy specification agree on the order."""
+    import oracle
+    from pangenomix_b200 import synth
+    coo = synth.bernoulli_matrix(6000, 1500, 450, seed=3)          # thousands of short rows, hundreds per class
+    balanced = build_host_plan(coo, long_threshold=100, perms_per_cta=8)
+    monkeypatch.setenv("PGX_NO_ROW_BALANCE", "1")
+    by_length = build_host_plan(coo, long_threshold=100, perms_per_cta=8)
+    monkeypatch.delenv("PGX_NO_ROW_BALANCE")
+    assert sorted(balanced.row_gene.tolist()) == sorted(by_length.row_gene.tolist())
+    assert np.array_equal(balanced.tasks[:, [0, 1, 3]], by_length.tasks[:, [0, 1, 3]])      # same sub-blocks, other rows in them
+    w_bal, w_len = check_layout(balanced), check_layout(by_length)
+    assert w_bal < w_len - 0.08 and w_bal < 1.06
+    perms = draw_perms(5, 1500, 2)
+    pan, core = oracle.pan_core_curves_minrank(coo, perms)
+    assert np.array_equal(curves_from_plan(balanced, perms), np.hstack([pan, core]).astype(np.int64))
+    monkeypatch.setenv("PGX_PLAN_NUMPY", "1")
+    spec = build_host_plan(coo, long_threshold=100, perms_per_cta=8)
+    monkeypatch.delenv("PGX_PLAN_NUMPY")
+    _plans_equal(balanced, spec)
+    # wide wavefront groups (16 and 32 lanes) and a window larger than a class
+    for b in (4, 2):
+        a = build_host_plan(coo, long_threshold=30, perms_per_cta=b)
+        monkeypatch.setenv("PGX_PLAN_NUMPY", "1")
+        c = build_host_plan(coo, long_threshold=30, perms_per_cta=b)
+        monkeypatch.delenv("PGX_PLAN_NUMPY")
+        _plans_equal(a, c)
+        check_layout(a)
