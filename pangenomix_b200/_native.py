@@ -9,7 +9,8 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libpgx_b200.so")
+# PGX_LIBRARY selects another build of the SAME library (scripts/sanitize_host.sh: host helpers under ASan/UBSan)
+LIB_PATH = os.environ.get("PGX_LIBRARY") or os.path.join(_HERE, "libpgx_b200.so")
 
 # every symbol include/pgx.h declares (tests check the library exports all of them)
 EXPORTS = (
