@@ -215,6 +215,14 @@ int pgx_plan_balance_rows(const int64_t *indptr, const int32_t *indices, const i
  * is 1" test for the int64 (value 1) and float64 (value = bits of 1.0) ``data`` arrays of a table. */
 int pgx_plan_all_equal_u64(const uint64_t *words, int64_t n, uint64_t value, int32_t n_threads);
 
+/* LSDF ingest (host): raw DEFLATE (RFC 1951) of one zip member straight into the caller's buffer.
+ * Replaces the zlib inflate inside scipy.sparse.load_npz, which read_lsdf calls
+ * (/root/reference/pangenomix/sparse_utils.py:35; the archive is written deflated at :314).
+ * dst_len must be the exact inflated size (the zip entry's file_size).  Returns PGX_ERR_INVALID for
+ * anything that is not a complete, well-formed stream of that size; the caller verifies the
+ * entry's CRC-32 and falls back to zlib on any error.  Thread-safe (no shared state). */
+int pgx_inflate_raw(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len);
+
 /* numpy legacy RandomState stream (host): ``count`` consecutive
  * ``a = np.arange(n); np.random.shuffle(a)`` results as uint16 rows, continuing from the
  * MT19937 state in ``mt_key`` (624 words) / ``mt_pos`` exactly as

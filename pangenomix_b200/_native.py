@@ -20,7 +20,7 @@ EXPORTS = (
     "pgx_legacy_shuffles", "pgx_profile_enable", "pgx_profile_read",
     "pgx_heaps_scratch_bytes", "pgx_heaps_fit", "pgx_estimate_pan_core",
     "pgx_plan_bank_order", "pgx_plan_build_bitmap", "pgx_plan_coo_to_csr", "pgx_plan_folded_lists",
-    "pgx_plan_missing_genome", "pgx_plan_all_equal_u64", "pgx_plan_balance_rows",
+    "pgx_plan_missing_genome", "pgx_plan_all_equal_u64", "pgx_plan_balance_rows", "pgx_inflate_raw",
 )
 
 
@@ -101,6 +101,8 @@ def load():
     lib.pgx_plan_balance_rows.argtypes = [vp, vp, vp, vp, vp, i64, i32, i32, i32, vp, i32]
     lib.pgx_plan_all_equal_u64.restype = ctypes.c_int
     lib.pgx_plan_all_equal_u64.argtypes = [vp, i64, ctypes.c_uint64, i32]
+    lib.pgx_inflate_raw.restype = ctypes.c_int
+    lib.pgx_inflate_raw.argtypes = [vp, i64, vp, i64]
     lib.pgx_estimate_pan_core.restype = ctypes.c_int
     lib.pgx_estimate_pan_core.argtypes = [plan_p, vp, ctypes.POINTER(i32), i64, vp, i64]
     lib.pgx_heaps_scratch_bytes.restype = ctypes.c_size_t

@@ -16,9 +16,26 @@ _ROW_AXES = ("index", 0)
 _COL_AXES = ("columns", 1)
 
 
+def _native_inflate(raw, size):
+    """``size`` bytes inflated from the raw DEFLATE stream ``raw`` by libpgx_b200's decoder (pgx_inflate_raw),
+    straight into a fresh writable uint8 array; None if the library is not built or rejects the stream."""
+    try:
+        from . import _native
+        lib = _native.load()
+    except Exception:                                  # host I/O keeps working without the CUDA library (zlib)
+        return None
+    out = np.empty(size, dtype=np.uint8)
+    src = np.frombuffer(raw, dtype=np.uint8)
+    if lib.pgx_inflate_raw(src.ctypes.data if src.size else None, src.size, out.ctypes.data if size else None, size) != 0:
+        return None
+    return out
+
+
 def _inflate_npy_member(path, info):
-    """One ``.npy`` member of an ``.npz`` archive as a writable array, inflated with a single zlib call
-    (which releases the GIL, so the members of an archive inflate side by side)."""
+    """One ``.npy`` member of an ``.npz`` archive as a writable array.  The member is inflated in one call that
+    releases the GIL (so the members of an archive inflate side by side): by libpgx_b200's DEFLATE decoder,
+    directly into the array's memory, or by zlib if that is unavailable or refuses the stream.  The zip
+    entry's CRC-32 is checked either way."""
     import io
     import struct
     import zipfile
@@ -31,21 +48,32 @@ def _inflate_npy_member(path, info):
         name_len, extra_len = struct.unpack("<HH", header[26:30])
         handle.seek(info.header_offset + 30 + name_len + extra_len)
         raw = handle.read(info.compress_size)
+    if len(raw) != info.compress_size:
+        raise ValueError("member %s is truncated" % info.filename)
+    data = None
     if info.compress_type == zipfile.ZIP_DEFLATED:
-        raw = zlib.decompress(raw, -15, max(1, info.file_size))
-    elif info.compress_type != zipfile.ZIP_STORED:
+        data = _native_inflate(raw, info.file_size)
+        if data is not None and (zlib.crc32(data) & 0xFFFFFFFF) != info.CRC:
+            data = None                                                           # let zlib have the last word
+        if data is None:
+            data = np.frombuffer(zlib.decompress(raw, -15, max(1, info.file_size)), dtype=np.uint8).copy()
+    elif info.compress_type == zipfile.ZIP_STORED:
+        data = np.frombuffer(raw, dtype=np.uint8).copy()
+    else:
         raise ValueError("unsupported compression")
-    if len(raw) != info.file_size or (zlib.crc32(raw) & 0xFFFFFFFF) != info.CRC:
+    if data.size != info.file_size or (zlib.crc32(data) & 0xFFFFFFFF) != info.CRC:
         raise ValueError("member %s is corrupt" % info.filename)
-    stream = io.BytesIO(raw)
+    stream = io.BytesIO(data[:min(data.size, 1 << 16)].tobytes())                 # the .npy header
     version = np.lib.format.read_magic(stream)
     read_header = {(1, 0): np.lib.format.read_array_header_1_0, (2, 0): np.lib.format.read_array_header_2_0}[version]
     shape, fortran, dtype = read_header(stream)
     if dtype.hasobject:
         raise ValueError("object arrays are not loaded")
     count = int(np.prod(shape, dtype=np.int64))
-    flat = np.frombuffer(raw, dtype=dtype, offset=stream.tell(), count=count)
-    return np.array(flat).reshape(shape, order="F" if fortran else "C")       # own, writable memory
+    flat = np.frombuffer(data, dtype=dtype, offset=stream.tell(), count=count)    # a writable view of ``data``
+    if not flat.flags.aligned:
+        flat = flat.copy()
+    return flat.reshape(shape, order="F" if fortran else "C")
 
 
 def _load_npz_coo(npz_file):

@@ -21,15 +21,24 @@ else
   LINK="-Xlinker $(gcc -print-file-name=libubsan.so)"
   PRE="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)"
 fi
-for src in pgx_rng pgx_plan; do
+for src in pgx_rng pgx_plan pgx_inflate; do
   g++ -O1 -g -std=c++17 -fPIC -pthread $SAN -I "$REPO/include" -c "$CSRC/$src.cpp" -o "$OUT/$src.o"
 done
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O3,-pthread -shared \
   -I "$REPO/include" -I "$CSRC" -o "$OUT/libpgx_b200.so" \
-  "$CSRC/pgx_api.cu" "$CSRC/pgx_rarefy.cu" "$CSRC/pgx_bernoulli.cu" "$CSRC/pgx_heaps.cu" "$OUT/pgx_rng.o" "$OUT/pgx_plan.o" \
+  "$CSRC/pgx_api.cu" "$CSRC/pgx_rarefy.cu" "$CSRC/pgx_bernoulli.cu" "$CSRC/pgx_heaps.cu" "$OUT/pgx_rng.o" "$OUT/pgx_plan.o" "$OUT/pgx_inflate.o" \
   $LINK
 cd "$REPO"
 if [ $# -eq 0 ]; then set -- tests/test_plan.py tests/test_abi_cpu.py tests/test_sparse_utils.py tests/test_distributed_cpu.py; fi
-LD_PRELOAD="$PRE" TSAN_OPTIONS=halt_on_error=0:report_signal_unsafe=0 \
-ASAN_OPTIONS=detect_leaks=0:abort_on_error=1:allocator_may_return_null=1 UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1 \
-PGX_LIBRARY="$OUT/libpgx_b200.so" python -m pytest "$@" -x -q -m "not gpu" -p no:cacheprovider
+# reports go to files: pytest captures stderr and a sanitizer exit inside a test would take the report with it
+rm -f "$OUT"/report.*
+RC=0
+LD_PRELOAD="$PRE" TSAN_OPTIONS=halt_on_error=0:report_signal_unsafe=0:log_path="$OUT/report" \
+ASAN_OPTIONS=detect_leaks=0:allocator_may_return_null=1:log_path="$OUT/report" \
+UBSAN_OPTIONS=print_stacktrace=1:halt_on_error=1:log_path="$OUT/report" \
+PGX_LIBRARY="$OUT/libpgx_b200.so" python -m pytest "$@" -x -q -m "not gpu" -p no:cacheprovider || RC=$?
+if ls "$OUT"/report.* > /dev/null 2>&1; then
+  echo "SANITIZER REPORTS:"; head -n 40 "$OUT"/report.*; exit 1
+fi
+echo "no sanitizer report"
+exit $RC

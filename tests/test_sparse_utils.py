@@ -111,3 +111,74 @@ def test_threaded_npz_loader_equals_scipy(tmp_path):
     import pytest
     with pytest.raises(Exception):
         scipy.sparse.load_npz(broken)
+
+
+def _deflate(data, level=6, strategy=0, wbits=-15):
+    import zlib
+    c = zlib.compressobj(level, zlib.DEFLATED, wbits, 9, strategy)
+    return c.compress(data) + c.flush()
+
+
+def test_native_inflate_equals_zlib():
+    """pgx_inflate_raw (csrc/pgx_inflate.cpp), the decoder behind read_lsdf: byte-identical to zlib on stored,
+    fixed and dynamic blocks, short distances, long runs, multi-block streams; wrong sizes and damaged streams
+    are refused or differ (the loader then checks the zip CRC and falls back to zlib)."""
+    import zlib
+    rng = np.random.RandomState(0)
+    cases = [b"", b"a", b"abc" * 5, bytes(1000),
+             bytes(rng.randint(0, 256, 70000, dtype=np.uint8)),                                   # stored blocks
+             bytes(rng.randint(0, 4, 200000, dtype=np.uint8)),
+             np.sort(rng.randint(0, 200000, 300000)).astype(np.int32).tobytes(),                  # a row member
+             np.repeat(np.arange(2000, dtype=np.int32), rng.randint(1, 300, 2000)).tobytes(),     # a col member
+             np.ones(200000, dtype=np.int64).tobytes(),                                           # a data member
+             b"ab" * 70000 + b"xyz" * 50000 + b"q" * 100000 + b"0123456" * 30000 + b"01234" * 999 + b"012345" * 999,
+             b" ".join(str(x).encode() for x in rng.randint(0, 10 ** 6, 100000))]
+    for data in cases:
+        for level in (0, 1, 6, 9):
+            for strategy in (zlib.Z_DEFAULT_STRATEGY, zlib.Z_FIXED, zlib.Z_HUFFMAN_ONLY, zlib.Z_RLE):
+                for wbits in (-15, -9):
+                    raw = _deflate(data, level, strategy, wbits)
+                    out = su._native_inflate(raw, len(data))
+                    assert out is not None and out.tobytes() == data and out.flags.writeable
+                    if len(data) > 10:
+                        assert su._native_inflate(raw, len(data) - 1) is None
+                        assert su._native_inflate(raw, len(data) + 1) is None
+                        assert su._native_inflate(raw[:len(raw) // 2], len(data)) is None
+    # a stream with sync / full flushes (empty stored blocks between compressed ones)
+    c, parts, data = zlib.compressobj(6, zlib.DEFLATED, -15), [], b""
+    for k in range(40):
+        chunk = bytes(rng.randint(0, 1 + k, rng.randint(1, 20000), dtype=np.uint8))
+        data += chunk
+        parts += [c.compress(chunk), c.flush(zlib.Z_SYNC_FLUSH if k % 2 else zlib.Z_FULL_FLUSH)]
+    raw = b"".join(parts) + c.flush()
+    assert su._native_inflate(raw, len(data)).tobytes() == data
+    # damaged streams never crash; whatever comes back differs from the original or is refused
+    big = np.sort(rng.randint(0, 200000, 100000)).astype(np.int32).tobytes()
+    raw = _deflate(big)
+    for _ in range(400):
+        hurt = bytearray(raw)
+        hurt[rng.randint(0, len(hurt))] ^= 1 << rng.randint(0, 8)
+        out = su._native_inflate(bytes(hurt), len(big))
+        assert out is None or zlib.crc32(out) != zlib.crc32(big) or out.tobytes() == big
+    for _ in range(200):                                                                           # random garbage
+        junk = bytes(rng.randint(0, 256, rng.randint(1, 400), dtype=np.uint8))
+        su._native_inflate(junk, int(rng.randint(0, 5000)))
+
+
+def test_read_lsdf_uses_the_native_decoder_and_falls_back(tmp_path, monkeypatch):
+    coo = synth.bernoulli_matrix(3000, 40, 300, seed=5)
+    labels = ["g%d" % i for i in range(3000)], ["s%d" % i for i in range(40)]
+    path = str(tmp_path / "t.npz")
+    su.LightSparseDataFrame(labels[0], labels[1], coo).to_npz(path)
+    calls = []
+    real = su._native_inflate
+    monkeypatch.setattr(su, "_native_inflate", lambda raw, size: calls.append(size) or real(raw, size))
+    fast = su.read_lsdf(path)
+    assert len(calls) == 5 and (fast.data.tocsr() != coo.tocsr()).nnz == 0          # row, col, data, shape, format
+    assert fast.data.row.flags.writeable and fast.data.data.dtype == np.int64
+    monkeypatch.setattr(su, "_native_inflate", lambda raw, size: None)              # library absent / refusing
+    slow = su.read_lsdf(path)
+    assert (slow.data.tocsr() != coo.tocsr()).nnz == 0 and slow.data.row.flags.writeable
+    wrong = lambda raw, size: np.zeros(size, dtype=np.uint8)                        # a wrong answer fails the CRC
+    monkeypatch.setattr(su, "_native_inflate", wrong)
+    assert (su.read_lsdf(path).data.tocsr() != coo.tocsr()).nnz == 0
