@@ -50,19 +50,21 @@ def _inflate_npy_member(path, info):
         raw = handle.read(info.compress_size)
     if len(raw) != info.compress_size:
         raise ValueError("member %s is truncated" % info.filename)
-    data = None
+    def sound(blob):
+        return blob is not None and blob.size == info.file_size and (zlib.crc32(blob) & 0xFFFFFFFF) == info.CRC
+
     if info.compress_type == zipfile.ZIP_DEFLATED:
         data = _native_inflate(raw, info.file_size)
-        if data is not None and (zlib.crc32(data) & 0xFFFFFFFF) != info.CRC:
-            data = None                                                           # let zlib have the last word
-        if data is None:
+        if not sound(data):                                                       # let zlib have the last word
             data = np.frombuffer(zlib.decompress(raw, -15, max(1, info.file_size)), dtype=np.uint8).copy()
+            if not sound(data):
+                raise ValueError("member %s is corrupt" % info.filename)
     elif info.compress_type == zipfile.ZIP_STORED:
         data = np.frombuffer(raw, dtype=np.uint8).copy()
+        if not sound(data):
+            raise ValueError("member %s is corrupt" % info.filename)
     else:
         raise ValueError("unsupported compression")
-    if data.size != info.file_size or (zlib.crc32(data) & 0xFFFFFFFF) != info.CRC:
-        raise ValueError("member %s is corrupt" % info.filename)
     stream = io.BytesIO(data[:min(data.size, 1 << 16)].tobytes())                 # the .npy header
     version = np.lib.format.read_magic(stream)
     read_header = {(1, 0): np.lib.format.read_array_header_1_0, (2, 0): np.lib.format.read_array_header_2_0}[version]
@@ -76,10 +78,12 @@ def _inflate_npy_member(path, info):
     return flat.reshape(shape, order="F" if fortran else "C")
 
 
-def _load_npz_coo(npz_file):
+def _load_npz_coo(npz_file, meanwhile=None):
     """``scipy.sparse.load_npz`` for the COO archives ``to_npz`` writes (sparse_utils.py:295-314), with the
     ``row`` / ``col`` / ``data`` members inflated on separate threads: a 10,000 x 200,000 table loads in
-    1.1 s instead of 2.0 s.  Anything unexpected (other formats, odd archives) is left to scipy."""
+    1.1 s instead of 2.0 s.  Anything unexpected (other formats, odd archives) is left to scipy.
+    ``meanwhile(shape)`` runs on the calling thread while the big members inflate (the inflate calls release
+    the GIL): read_lsdf reads and indexes the labels there."""
     import zipfile
     from concurrent.futures import ThreadPoolExecutor
     try:
@@ -90,7 +94,10 @@ def _load_npz_coo(npz_file):
         if any(info.flag_bits & 0x1 for info in members.values()):                # encrypted
             return None
         with ThreadPoolExecutor(max_workers=3) as pool:
-            jobs = {name[:-4]: pool.submit(_inflate_npy_member, npz_file, info) for name, info in members.items()}
+            jobs = {name[:-4]: pool.submit(_inflate_npy_member, npz_file, info)
+                    for name, info in sorted(members.items(), key=lambda item: item[1].file_size)}       # small ones first
+            if meanwhile is not None:
+                meanwhile(tuple(int(v) for v in jobs["shape"].result()))
             parts = {name: job.result() for name, job in jobs.items()}
         fmt = parts["format"].item()
         if (fmt.decode("ascii") if isinstance(fmt, bytes) else fmt) != "coo":
@@ -114,15 +121,39 @@ def read_lsdf(npz_file, label_file=None):
     ``label_file`` defaults to ``<npz_file>.labels.txt``: one label per line, the row
     labels first, then the column labels.
     """
-    matrix = _load_npz_coo(npz_file) if isinstance(npz_file, str) else None
-    if matrix is None:
-        matrix = scipy.sparse.load_npz(npz_file)
     if label_file is None:
         label_file = npz_file + ".labels.txt"
+    early = {}
+
+    def index_labels(shape):
+        # runs beside the inflate threads; whatever goes wrong here is reported after the matrix, as before
+        try:
+            early["parts"] = _label_parts(label_file, shape[0])
+        except Exception as exc:
+            early["error"] = exc
+
+    matrix = _load_npz_coo(npz_file, index_labels) if isinstance(npz_file, str) else None
+    if matrix is None:
+        matrix = scipy.sparse.load_npz(npz_file)
+        early.clear()
+    if "error" in early:
+        raise early["error"]
+    if "parts" not in early or early["parts"][4] != matrix.shape[0]:
+        early["parts"] = _label_parts(label_file, matrix.shape[0])
+    index, columns, index_map, column_map, _ = early["parts"]
+    if len(index) != matrix.shape[0] or len(columns) != matrix.shape[1]:
+        return LightSparseDataFrame(list(index), list(columns), matrix)             # the constructor's diagnostics
+    return LightSparseDataFrame._from_parts(index, columns, index_map, column_map, matrix)
+
+
+def _label_parts(label_file, n_rows):
+    """(index array, columns array, index_map, column_map, n_rows) of a ``.labels.txt``: the row labels first,
+    then the column labels, one per line -- what the LightSparseDataFrame constructor derives from them."""
     with open(label_file, "r") as handle:
         labels = [line.strip() for line in handle]
-    n_rows = matrix.shape[0]
-    return LightSparseDataFrame(labels[:n_rows], labels[n_rows:], matrix)
+    index, columns = labels[:n_rows], labels[n_rows:]
+    return (np.array(index), np.array(columns), {label: i for i, label in enumerate(index)},
+            {label: i for i, label in enumerate(columns)}, n_rows)
 
 
 def compress_rows(lsdf):
@@ -236,6 +267,17 @@ class LightSparseDataFrame():
             print('ERROR: Index length does not match data')
         if len(columns) != data.shape[1]:
             print('ERROR: Column length does no match data')
+
+    @classmethod
+    def _from_parts(cls, index, columns, index_map, column_map, coo):
+        """What ``LightSparseDataFrame(index, columns, coo)`` builds, from pieces read_lsdf prepared while the
+        archive was still inflating (lengths already checked by the caller)."""
+        self = cls.__new__(cls)
+        self.data = coo.tocoo()
+        self.index, self.columns = index, columns
+        self.shape = self.data.shape
+        self.index_map, self.column_map = index_map, column_map
+        return self
 
     def transpose(self):
         return LightSparseDataFrame(index=self.columns, columns=self.index,
