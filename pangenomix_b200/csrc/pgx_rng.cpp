@@ -48,6 +48,8 @@ struct Mt19937 {
     int pos;                                        // next word: 0 .. 624, or negative while carried words remain
     bool avx2;
     bool avx512 = false;
+    bool bmi2 = false;
+    bool carried = false;                           // the current block was entered through carry_tail
 
     static inline uint32_t twist(uint32_t a, uint32_t b, uint32_t far)
     {
@@ -168,10 +170,12 @@ struct Mt19937 {
         refill();
         memcpy(out - rem, tail, sizeof(uint32_t) * rem);
         pos = -rem;
+        carried = true;
     }
 
     void refill()
     {
+        carried = false;
 #if PGX_X86
         if (avx512) {
             refill_avx512();
@@ -359,6 +363,64 @@ void accept_avx512_span32(Mt19937 &mt, uint32_t &i_io, uint32_t lo, uint32_t mas
 }
 #endif
 
+#if PGX_X86
+// The end of a mask regime (fewer than 32 accepts left under this mask, down to the last one) and the small
+// regimes at the end of a shuffle, 16 draws per step: the lanes are settled as in accept_avx512_span32, then
+// the step is cut behind the accept that ends the regime (its position is the r-th set bit of the accept mask:
+// PDEP) and only the draws up to there are consumed -- the next regime starts on the very next draw with its
+// own mask.  Replaces the draw-by-draw scalar loop for the ~250 draws per shuffle that no full step covers.
+__attribute__((target("avx512f,popcnt,bmi2")))
+void accept_avx512_tail(Mt19937 &mt, uint32_t &i_io, uint32_t lo, uint32_t mask, uint32_t *&w_io)
+{
+    uint32_t i = i_io;
+    uint32_t *w = w_io;
+    int pos = mt.pos;
+    const __m512i maskv = _mm512_set1_epi32(static_cast<int>(mask));
+    const __m512i iota = _mm512_setr_epi32(0, 1, 2, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 14, 15);
+    while (i >= lo) {
+        if (pos + 16 > 624) {
+            mt.pos = pos;
+            if (pos >= 624) mt.refill(); else mt.carry_tail();
+            pos = mt.pos;
+            continue;
+        }
+        const __m512i v = _mm512_and_si512(_mm512_loadu_si512(mt.out + pos), maskv);
+        const __m512i top_v = _mm512_set1_epi32(static_cast<int>(i));
+        // lane l is tested against i - (accepts before it) >= max(i - l, lo) > 0 as long as it lies before the cut
+        const __m512i floor_v = _mm512_sub_epi32(_mm512_max_epu32(top_v, iota), iota);
+        const unsigned over = _mm512_cmpgt_epu32_mask(v, top_v);
+        unsigned acc = _mm512_cmple_epu32_mask(v, floor_v);
+        unsigned doubt = ~(acc | over) & 0xffffu;
+        if (doubt) {
+            alignas(64) uint32_t lanes[16];
+            _mm512_store_si512(lanes, v);
+            do {
+                const int l = __builtin_ctz(doubt);
+                doubt &= doubt - 1;
+                const uint32_t before = static_cast<uint32_t>(_mm_popcnt_u32(acc & ((1u << l) - 1u)));
+                // (a lane behind the cut may see before > i: whatever it decides is cut away below)
+                if (lanes[l] <= i - before) acc |= 1u << l;
+            } while (doubt);
+        }
+        const uint32_t left = i - lo + 1;                          // accepts left under this mask, >= 1
+        int use = 16;
+        if (static_cast<uint32_t>(_mm_popcnt_u32(acc)) >= left) {
+            const int last = __builtin_ctz(_pdep_u32(1u << (left - 1), acc));
+            use = last + 1;
+            acc &= (2u << last) - 1u;
+        }
+        _mm512_storeu_si512(w, _mm512_maskz_compress_epi32(static_cast<__mmask16>(acc), v));
+        const uint32_t got = static_cast<uint32_t>(_mm_popcnt_u32(acc));
+        w += got;
+        i -= got;
+        pos += use;
+    }
+    mt.pos = pos;
+    i_io = i;
+    w_io = w;
+}
+#endif
+
 void accept_one(Mt19937 &mt, uint32_t n, uint32_t *js)
 {
     if (n < 2) return;
@@ -369,6 +431,11 @@ void accept_one(Mt19937 &mt, uint32_t n, uint32_t *js)
         const uint32_t mask = 0xffffffffu >> (32 - bits);          // smallest 2^b - 1 >= i
         const uint32_t lo = 1u << (bits - 1);                      // the mask holds while i >= lo
 #if PGX_X86
+        if (mt.avx512 && mt.bmi2 && mask < 0x80000000u) {
+            accept_avx512_span32(mt, i, lo, mask, w);              // 32 draws per step while >= 32 accepts remain
+            accept_avx512_tail(mt, i, lo, mask, w);                // ... and the end of the regime, cut at its last accept
+            continue;
+        }
         if (mt.avx2 && mask < 0x80000000u) {
             // alternate: vector spans while far from lo and unambiguous, scalar for what is left
             const uint32_t stretch = mt.avx512 ? 16 : 8;
@@ -459,12 +526,15 @@ extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n,
     Mt19937 &mt = mt_storage;
     memcpy(mt.key, mt_key, sizeof(uint32_t) * 624);
     mt.pos = *mt_pos;
+    mt.carried = false;
 #if PGX_X86
     mt.avx2 = __builtin_cpu_supports("avx2") && __builtin_cpu_supports("popcnt") && !getenv("PGX_RNG_SCALAR");
     mt.avx512 = mt.avx2 && __builtin_cpu_supports("avx512f") && !getenv("PGX_RNG_NO_AVX512");
+    mt.bmi2 = mt.avx512 && __builtin_cpu_supports("bmi2") && !getenv("PGX_RNG_NO_TAIL");
 #else
     mt.avx2 = false;
     mt.avx512 = false;
+    mt.bmi2 = false;
 #endif
     mt.temper_scalar();
 
@@ -546,7 +616,8 @@ extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n,
         cv_work.notify_all();
         for (auto &th : pool) th.join();
     }
-    if (mt.pos < 0) {                              // the call ended inside a carried block tail
+    if (mt.pos < 0 || (mt.pos == 0 && mt.carried)) {   // the call ended inside (or exactly at the end of) a carried block tail:
+                                                       // numpy is still on the old block, at position 624 - remaining
         memcpy(mt_key, mt.prev_key, sizeof(uint32_t) * 624);
         *mt_pos = 624 + mt.pos;
     } else {

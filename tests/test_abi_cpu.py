@@ -129,3 +129,29 @@ def test_no_cuda_means_loud_failure(have_cuda):
         engine.PanCoreEngine(scipy.sparse.coo_matrix(np.eye(4, dtype=np.int64)))
     with pytest.raises(_native.PgxError):
         engine.BernoulliGrid(np.eye(4))
+
+
+@pytest.mark.parametrize("mode", ["", "PGX_RNG_NO_TAIL", "PGX_RNG_NO_AVX512"])
+def test_legacy_shuffles_state_at_every_block_position(monkeypatch, mode):
+    """Short calls started from every region of the MT19937 block: the permutations AND the exported state
+    (key and position, as np.random.get_state() reports them) equal numpy's.  The vector steps read up to 32
+    words ahead and carry block tails in front of the next block, so a call may end inside a carried tail or
+    exactly at its end -- numpy is then still on the old block (position 624 - remaining, or 624)."""
+    if mode:
+        monkeypatch.setenv(mode, "1")
+    for n in (33, 40, 47, 64, 65, 97, 100, 129, 400, 1000):
+        for skip in range(0, 700, 7):
+            np.random.seed(1000 + skip)
+            if skip:
+                np.random.randint(0, 2 ** 31 - 1, size=skip)          # moves the position inside the block
+            start = np.random.get_state()
+            count = 1 + skip % 3
+            got = engine.draw_legacy_permutations(n, count)
+            ours = np.random.get_state()
+            np.random.set_state(start)
+            for i in range(count):
+                a = np.arange(n)
+                np.random.shuffle(a)
+                assert np.array_equal(a, got[i]), (n, skip, i)
+            theirs = np.random.get_state()
+            assert ours[2] == theirs[2] and np.array_equal(ours[1], theirs[1]), (n, skip, ours[2], theirs[2])
