@@ -13,8 +13,11 @@
 #include <stdint.h>
 #include <stdlib.h>
 #include <string.h>
+#include <unistd.h>
 
 #include <algorithm>
+#include <atomic>
+#include <chrono>
 #include <condition_variable>
 #include <deque>
 #include <mutex>
@@ -510,6 +513,148 @@ int worker_threads_wanted()
     return static_cast<int>(std::min(4u, hw > 1 ? hw - 1 : 0u));
 }
 
+// Stage-3 workers, created on first use and kept (see pgx_legacy_shuffles).  Batches are handed over through
+// atomics, not a condition variable: waking a sleeping thread costs 0.2-0.5 ms on the virtualised hosts this
+// runs on (measured: 17 submits of a 209-shuffle call took 8 ms, three times the acceptance work itself), so
+// idle workers spin for a few milliseconds -- long enough to stay awake from one block-sized call to the next
+// -- before they go to sleep, and the producer only pays for a wake-up when somebody is in fact asleep.
+// The object is leaked on purpose: at process exit its threads must not see it destroyed.
+class WorkerPool {
+public:
+    static constexpr int MAX_THREADS = 16;
+    static constexpr int MAX_SLOTS = 2 * MAX_THREADS + 2;
+
+    static WorkerPool &get(int threads)
+    {
+        static WorkerPool *pool = nullptr;
+        if (!pool || pool->pid_ != getpid()) pool = new WorkerPool();     // a forked child has no threads: start over
+        pool->grow(threads);
+        return *pool;
+    }
+
+    // Call context; only the producer calls begin / slot_for_next / submit / finish, one call at a time, and
+    // every batch of the previous call is complete when begin runs.
+    void begin(uint32_t n, size_t stride, uint32_t *ring, int batch, int n_slots, uint16_t *perms, int active)
+    {
+        n_ = n;
+        stride_ = stride;
+        ring_ = ring;
+        batch_ = batch;
+        perms_ = perms;
+        n_slots_ = n_slots;
+        base_ = produced_.load(std::memory_order_relaxed);
+        for (int s = 0; s < n_slots; ++s) slot_done_[s].store(base_, std::memory_order_relaxed);
+        active_.store(active, std::memory_order_release);
+    }
+
+    // Buffer of the next batch: its slot is free once the batch that used it n_slots batches ago is complete.
+    int slot_for_next()
+    {
+        const int64_t id = produced_.load(std::memory_order_relaxed);
+        const int s = static_cast<int>((id - base_) % n_slots_);
+        while (slot_done_[s].load(std::memory_order_acquire) < id - n_slots_ + 1) {
+            if (!run_one()) cpu_relax();                                   // the producer helps instead of waiting
+        }
+        return s;
+    }
+
+    void submit(int slot, int64_t first, int count)
+    {
+        jobs_[slot].first = first;
+        jobs_[slot].count = count;
+        produced_.fetch_add(1, std::memory_order_seq_cst);                 // publishes the job and the call context
+        if (sleepers_.load(std::memory_order_seq_cst) > 0) {
+            { std::lock_guard<std::mutex> lock(mu_); }
+            cv_.notify_all();
+        }
+    }
+
+    void finish()
+    {
+        while (run_one()) {}
+        const int64_t all = produced_.load(std::memory_order_relaxed);
+        while (completed_.load(std::memory_order_acquire) < all) cpu_relax();
+    }
+
+private:
+    struct Job { int64_t first = 0; int count = 0; };
+
+    WorkerPool() : pid_(getpid()) {}
+
+    static inline void cpu_relax()
+    {
+#if PGX_X86
+        _mm_pause();
+#endif
+    }
+
+    void grow(int threads)
+    {
+        threads = std::min(threads, MAX_THREADS);
+        while (n_threads_ < threads) {
+            const int idx = n_threads_++;
+            std::thread([this, idx] { work(idx); }).detach();
+        }
+    }
+
+    // Claims and applies one submitted batch; false if none is waiting.
+    bool run_one()
+    {
+        int64_t id = claimed_.load(std::memory_order_relaxed);
+        for (;;) {
+            if (id >= produced_.load(std::memory_order_acquire)) return false;
+            if (claimed_.compare_exchange_weak(id, id + 1, std::memory_order_acq_rel, std::memory_order_relaxed)) break;
+        }
+        const int s = static_cast<int>((id - base_) % n_slots_);
+        const Job job = jobs_[s];
+        apply_batch(n_, stride_, ring_ + stride_ * batch_ * s, perms_ + static_cast<size_t>(job.first) * n_, job.count);
+        slot_done_[s].store(id + 1, std::memory_order_release);
+        completed_.fetch_add(1, std::memory_order_release);
+        return true;
+    }
+
+    void work(int idx)
+    {
+        auto last_work = std::chrono::steady_clock::now();
+        unsigned rounds = 0;
+        for (;;) {
+            if (idx < active_.load(std::memory_order_acquire) && run_one()) {
+                last_work = std::chrono::steady_clock::now();
+                continue;
+            }
+            cpu_relax();
+            if ((++rounds & 255u) || std::chrono::steady_clock::now() - last_work < std::chrono::milliseconds(SPIN_MS)) continue;
+            // nothing for a few milliseconds: sleep until the producer submits again (the timeout is a safety net)
+            {
+                std::unique_lock<std::mutex> lock(mu_);
+                sleepers_.fetch_add(1, std::memory_order_seq_cst);
+                if (claimed_.load(std::memory_order_seq_cst) >= produced_.load(std::memory_order_seq_cst) ||
+                    idx >= active_.load(std::memory_order_acquire))
+                    cv_.wait_for(lock, std::chrono::milliseconds(200));
+                sleepers_.fetch_sub(1, std::memory_order_seq_cst);
+            }
+            last_work = std::chrono::steady_clock::now();
+        }
+    }
+
+    static constexpr int SPIN_MS = 3;                   // idle spinning before a worker goes to sleep
+
+    // call context (plain: published by the first submit of the call, read only after a claim)
+    uint32_t n_ = 0;
+    size_t stride_ = 0;
+    uint32_t *ring_ = nullptr;
+    uint16_t *perms_ = nullptr;
+    int batch_ = 0, n_slots_ = 1, n_threads_ = 0;
+    int64_t base_ = 0;
+    Job jobs_[MAX_SLOTS];
+    std::atomic<int64_t> slot_done_[MAX_SLOTS] = {};
+    std::atomic<int64_t> produced_{0}, claimed_{0}, completed_{0};
+    std::atomic<int> active_{0}, sleepers_{0};
+    std::mutex mu_;
+    std::condition_variable cv_;
+    const pid_t pid_;
+};
+
 }  // namespace
 
 extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n, int64_t count,
@@ -556,65 +701,26 @@ extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n,
             apply_one(un, js.data(), h_perms + t * n);
         }
     } else {
-        // producer (this thread): stages 1-2 into a ring of batch buffers; workers: stage 3
-        // The ring's buffers outlive the call (guarded by call_mu): a caller that draws block after block
-        // (pgx_estimate_pan_core) would otherwise pay for zero-filling ~5 MB of fresh pages per call.
-        struct Slot { uint32_t *js = nullptr; int64_t first = 0; int count = 0; };
+        // producer (this thread): stages 1-2 into a ring of batch buffers; workers: stage 3.
+        // The ring's buffers and the worker threads outlive the call (guarded by call_mu): a caller that draws
+        // block after block (pgx_estimate_pan_core, 209 shuffles per call) would otherwise pay for zero-filling
+        // ~5 MB of fresh pages per call and, far worse, for freshly created threads that the scheduler wakes on
+        // the producer's own core until its load balancer has spread them (measured on the build host: 38 us
+        // per shuffle in calls of 209 against 14 us in one long call, all of it in the producer's loop).
+        workers = std::min(workers, WorkerPool::MAX_THREADS);
+        WorkerPool &pool = WorkerPool::get(workers);
         const int n_slots = 2 * workers + 2;
         static std::vector<uint32_t> ring;
         if (ring.size() < stride * batch * n_slots) ring.resize(stride * batch * n_slots);
-        std::vector<Slot> slots(n_slots);
-        for (int s = 0; s < n_slots; ++s) slots[s].js = ring.data() + stride * batch * s;
-        std::mutex mu;
-        std::condition_variable cv_work, cv_free;
-        std::deque<int> ready, free_slots;
-        for (int s = 0; s < n_slots; ++s) free_slots.push_back(s);
-        bool done = false;
-        std::vector<std::thread> pool;
-        for (int w = 0; w < workers; ++w) {
-            pool.emplace_back([&]() {
-                for (;;) {
-                    int s;
-                    {
-                        std::unique_lock<std::mutex> lock(mu);
-                        cv_work.wait(lock, [&] { return done || !ready.empty(); });
-                        if (ready.empty()) return;
-                        s = ready.front();
-                        ready.pop_front();
-                    }
-                    apply_batch(un, stride, slots[s].js, h_perms + slots[s].first * n, slots[s].count);
-                    {
-                        std::lock_guard<std::mutex> lock(mu);
-                        free_slots.push_back(s);
-                    }
-                    cv_free.notify_one();
-                }
-            });
-        }
+        pool.begin(un, stride, ring.data(), batch, n_slots, h_perms, workers);
         for (int64_t t = 0; t < count; t += batch) {
-            int s;
-            {
-                std::unique_lock<std::mutex> lock(mu);
-                cv_free.wait(lock, [&] { return !free_slots.empty(); });
-                s = free_slots.front();
-                free_slots.pop_front();
-            }
+            const int s = pool.slot_for_next();
             const int c = static_cast<int>(std::min<int64_t>(batch, count - t));
-            for (int b = 0; b < c; ++b) accept_one(mt, un, slots[s].js + b * stride);
-            slots[s].first = t;
-            slots[s].count = c;
-            {
-                std::lock_guard<std::mutex> lock(mu);
-                ready.push_back(s);
-            }
-            cv_work.notify_one();
+            uint32_t *js = ring.data() + stride * batch * s;
+            for (int b = 0; b < c; ++b) accept_one(mt, un, js + b * stride);
+            pool.submit(s, t, c);
         }
-        {
-            std::lock_guard<std::mutex> lock(mu);
-            done = true;
-        }
-        cv_work.notify_all();
-        for (auto &th : pool) th.join();
+        pool.finish();                                   // the producer applies what is still queued, then waits
     }
     if (mt.pos < 0 || (mt.pos == 0 && mt.carried)) {   // the call ended inside (or exactly at the end of) a carried block tail:
                                                        // numpy is still on the old block, at position 624 - remaining

@@ -155,3 +155,36 @@ def test_legacy_shuffles_state_at_every_block_position(monkeypatch, mode):
                 assert np.array_equal(a, got[i]), (n, skip, i)
             theirs = np.random.get_state()
             assert ours[2] == theirs[2] and np.array_equal(ours[1], theirs[1]), (n, skip, ours[2], theirs[2])
+
+
+def test_legacy_shuffles_worker_pool_reuse_sleep_and_fork(monkeypatch):
+    """The stage-3 workers are a persistent pool that spins between calls and sleeps after a few idle
+    milliseconds: back-to-back calls with changing sizes and thread counts, pauses that put the workers to
+    sleep, and a forked child (which has no threads and must start its own pool) all give numpy's stream."""
+    import time
+    rng = np.random.RandomState(5)
+    for rep in range(40):
+        n = int(rng.choice([64, 100, 400, 1000, 4097, 10000]))
+        count = int(rng.randint(1, 300))
+        monkeypatch.setenv("PGX_RNG_THREADS", str(int(rng.choice([0, 1, 2, 4, 7, 16, 40]))))
+        seed = int(rng.randint(1 << 30))
+        np.random.seed(seed)
+        got = engine.draw_legacy_permutations(n, count)
+        ours = np.random.get_state()
+        assert np.array_equal(got, draw_perms(seed, n, count).astype(np.uint16))
+        theirs = np.random.get_state()
+        assert ours[2] == theirs[2] and np.array_equal(ours[1], theirs[1])
+        if rep % 10 == 0:
+            time.sleep(0.05)                     # > the 3 ms the workers spin before they sleep
+    monkeypatch.setenv("PGX_RNG_THREADS", "4")
+    np.random.seed(3)
+    want = engine.draw_legacy_permutations(1000, 300)
+    import warnings
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore", DeprecationWarning)
+        pid = os.fork()
+    if pid == 0:
+        np.random.seed(3)
+        os._exit(0 if np.array_equal(engine.draw_legacy_permutations(1000, 300), want) else 1)
+    _, status = os.waitpid(pid, 0)
+    assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
