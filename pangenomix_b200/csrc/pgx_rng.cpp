@@ -623,7 +623,7 @@ private:
                 continue;
             }
             cpu_relax();
-            if ((++rounds & 255u) || std::chrono::steady_clock::now() - last_work < std::chrono::milliseconds(SPIN_MS)) continue;
+            if ((++rounds & 255u) || std::chrono::steady_clock::now() - last_work < std::chrono::milliseconds(spin_ms_)) continue;
             // nothing for a few milliseconds: sleep until the producer submits again (the timeout is a safety net)
             {
                 std::unique_lock<std::mutex> lock(mu_);
@@ -637,7 +637,8 @@ private:
         }
     }
 
-    static constexpr int SPIN_MS = 3;                   // idle spinning before a worker goes to sleep
+    // idle spinning before a worker goes to sleep (PGX_RNG_SPIN_MS; 0 = sleep at once and pay for every wake-up)
+    const int spin_ms_ = getenv("PGX_RNG_SPIN_MS") ? std::max(0, atoi(getenv("PGX_RNG_SPIN_MS"))) : 3;
 
     // call context (plain: published by the first submit of the call, read only after a claim)
     uint32_t n_ = 0;
