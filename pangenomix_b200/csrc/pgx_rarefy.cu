@@ -33,6 +33,7 @@
 #include <sys/mman.h>
 #include <unistd.h>
 
+#include <atomic>
 #include <chrono>
 #include <condition_variable>
 #include <mutex>
@@ -946,12 +947,22 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
     std::mutex mu;
     std::condition_variable cv;
     long long issued = 0, retired = 0;
+    // EXPERIMENT, off unless PGX_ESTIMATE_SPIN=1 (never run on a GPU yet): the two sides poll atomic copies of the
+    // counters instead of sleeping on the condition variable -- a notify that finds a sleeper costs the notifier
+    // 0.2-0.5 ms on the virtualised hosts this runs on.
+    const bool spin = getenv("PGX_ESTIMATE_SPIN") != nullptr;
+    std::atomic<long long> a_issued{0}, a_retired{0};
+    auto publish = [&](bool wake) {                    // call with ``mu`` released
+        if (!spin || wake) cv.notify_all();
+    };
     int producer_rc = PGX_OK;
     char producer_err[512] = "";
     std::thread producer([&]() {
         cudaSetDevice(dev);
         for (long long k = 0; k < n_blocks; ++k) {
-            {
+            if (spin) {
+                while (a_retired.load(std::memory_order_acquire) + 3 <= k) std::this_thread::yield();
+            } else {
                 std::unique_lock<std::mutex> lk(mu);
                 cv.wait(lk, [&] { return retired + 3 > k; });
             }
@@ -974,8 +985,9 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
                     snprintf(producer_err, sizeof(producer_err), "%s", pgx_last_error());   // thread-local text
                 }
                 issued = rc ? n_blocks : k + 1;
+                a_issued.store(issued, std::memory_order_release);
             }
-            cv.notify_all();
+            publish(false);
             if (rc) return;
         }
     });
@@ -983,9 +995,12 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
     int copy_threads = std::max(1, std::min(6, static_cast<int>(std::thread::hardware_concurrency()) / 2));
     if (const char *env = getenv("PGX_COPY_THREADS")) copy_threads = std::max(1, std::min(16, atoi(env)));
     for (long long k = 0; k < n_blocks; ++k) {
+        if (spin) {
+            while (a_issued.load(std::memory_order_acquire) <= k) std::this_thread::yield();
+        }
         {
             std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return issued > k; });
+            cv.wait(lk, [&] { return issued > k; });         // (already true when spinning)
             if (producer_rc) break;
         }
         pgx::EstimateSlot &s = buf.slot[k % 3];
@@ -994,6 +1009,7 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
             rc = pgx::fail(PGX_ERR_CUDA, "a block of curves failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
             std::lock_guard<std::mutex> lk(mu);
             retired = n_blocks + 3;                     // let the producer run out
+            a_retired.store(retired, std::memory_order_release);
             cv.notify_all();
             break;
         }
@@ -1016,13 +1032,15 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
         {
             std::lock_guard<std::mutex> lk(mu);
             retired = k + 1;
+            a_retired.store(retired, std::memory_order_release);
         }
-        cv.notify_all();
+        publish(false);
         if (trace) fprintf(stderr, "[pgx trace] block %lld: on the host %.2f ms, copied out %.2f ms\n", k, t_ready, since());
     }
     {
         std::lock_guard<std::mutex> lk(mu);
         retired = n_blocks + 3;
+        a_retired.store(retired, std::memory_order_release);
     }
     cv.notify_all();
     producer.join();

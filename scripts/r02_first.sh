@@ -37,6 +37,16 @@ timeout 600 python bench.py > "$OUT/bench_c4_n1.json" 2> "$OUT/bench_c4_n1.err"
 step "bench c4 PGX_NO_ROW_BALANCE=1"
 PGX_NO_ROW_BALANCE=1 timeout 600 python bench.py --no-cpu-baseline --steps 10 > "$OUT/bench_c4_n1_no_balance.json" 2> "$OUT/bench_c4_n1_no_balance.err"
 
+# 4b. the reference-facing call after the CPU-only changes of round 1's last session (shuffle stream: 32-draw steps,
+#     PDEP regime ends, persistent spinning worker pool): estimate(2000) on C4 was 29 ms; then the opt-in spin
+#     hand-off of pgx_estimate_pan_core (PGX_ESTIMATE_SPIN=1, never run on a GPU before) and the old wake-up
+#     behaviour of the pool (PGX_RNG_SPIN_MS=0) for the A/B; the per-block timeline of the default
+step "probe_api c4 (default / PGX_ESTIMATE_SPIN=1 / PGX_RNG_SPIN_MS=0 / trace)"
+timeout 300 python scripts/probe_api.py c4 2000 > "$OUT/probe_api_c4.log" 2>&1
+PGX_ESTIMATE_SPIN=1 timeout 300 python scripts/probe_api.py c4 2000 > "$OUT/probe_api_c4_estimate_spin.log" 2>&1
+PGX_RNG_SPIN_MS=0 timeout 300 python scripts/probe_api.py c4 2000 > "$OUT/probe_api_c4_pool_sleeps.log" 2>&1
+PGX_ESTIMATE_TRACE=1 timeout 300 python scripts/probe_estimate_trace.py > "$OUT/estimate_trace_c4.log" 2>&1
+
 # 5. ncu: launch list, then one full capture of the two row kernels (each after a plain run of the same command).
 #    The counter that decides the A/B: l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld per LDS.128 of
 #    list_kernel<8> (5.27 in profiles/r01f_*; the layout model says 4.08 x measured/model ratio of round 1).
