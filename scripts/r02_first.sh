@@ -2,7 +2,7 @@
 # The first GPU call of the next round, as ONE command: everything round 1 left unmeasured
 # when its GPU budget ran out, ordered so that a call cut short still leaves the most useful files behind.
 #
-#   gpurun --timeout 2400 -- 'bash scripts/r02_first.sh'          (1 GPU, about 25 box-minutes)
+#   gpurun --timeout 3000 -- 'bash scripts/r02_first.sh'          (1 GPU, about 35 box-minutes)
 #
 # Every log lands under gpurun_out/r02_first/.  Nothing here reads /root/reference or the oracle except the
 # test suite (its checker) and bench.py's CPU arm.  No number printed by a run under ncu is a bench value.
