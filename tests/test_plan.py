@@ -258,3 +258,19 @@ def test_plan_row_balance_lowers_bank_conflicts(monkeypatch):
         monkeypatch.delenv("PGX_PLAN_NUMPY")
         _plans_equal(a, c)
         check_layout(a)
+
+
+def test_plan_wide_table_two_permutations_per_cta_with_row_balance():
+    """A C5-like width (50,000 genomes: 2 permutations per CTA, 32-lane wavefront groups, bitmap rows and list
+    rows side by side) through the planner's native helpers with the residue-balanced row order: the layout
+    invariants hold and the emulated kernels reproduce the oracle's curves."""
+    from oracle import cport
+    from pangenomix_b200 import synth
+    coo = synth.bernoulli_matrix(6000, 50000, 160, seed=11)
+    hp = build_host_plan(coo)
+    assert hp.perms_per_cta == 2 and hp.n_rows > 1000 and hp.n_long > 1000
+    assert check_layout(hp) < 1.2                       # wavefronts per gather step (1.38 for rows sorted by length on C5)
+    rng = np.random.RandomState(3)
+    perms = np.stack([rng.permutation(50000) for _ in range(2)])
+    pan, core = cport.curves_direct(coo, perms.astype(np.int32), n_threads=2)
+    assert np.array_equal(curves_from_plan(hp, perms), np.hstack([pan, core]).astype(np.int64))
