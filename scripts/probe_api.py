@@ -7,7 +7,8 @@ from pangenomix_b200 import _native, engine, synth
 
 name = sys.argv[1] if len(sys.argv) > 1 else "c4"
 iters = int(sys.argv[2]) if len(sys.argv) > 2 else 2000
-coo = synth.config_matrix(name)
+import bench
+coo = bench.load_matrix(name, 0, lambda: None)       # cached in /tmp per box
 eng = engine.PanCoreEngine(coo)
 n = eng.n_genomes
 np.random.seed(1)

@@ -3,7 +3,8 @@
 
 Run in the build container only (the reference does not exist on the GPU box):
 
-    python tests/golden/make_golden.py
+    python tests/golden/make_golden.py            # the round-1 fixtures
+    python tests/golden/make_golden.py --big      # the full-size fixtures of round 2 (C2, C4, C3; ~3 min)
 
 The reference has no tests or golden vectors of its own, so
 these fixtures -- outputs of the unmodified reference functions under a fixed
@@ -122,7 +123,53 @@ def edge_matrix():
     return scipy.sparse.coo_matrix(x)
 
 
+def big_cases(manifest):
+    """Round-2 additions: live-reference fixtures at the sizes the performance claims are made on.
+
+    c2_40000x400      config C2 in full, 64 of its 1,000 permutations (the reference needs 0.15 s each)
+    c4_200000x10000   config C4 in full, 4 of its 10,000 permutations (the reference needs ~12 s each)
+    bernoulli_c3_4000x400  config C3 (candidate-core size): the whole L-BFGS-B fit of the reference (~10 s)
+    The matrices are regenerated by pangenomix_b200.synth in the tests and checked against the stored digest.
+    """
+    c2 = synth.config_matrix("c2")
+    save_curve_case("c2_40000x400", c2, 12345, 64, store_matrix=False, heaps=True)
+    c4 = synth.config_matrix("c4")
+    save_curve_case("c4_200000x10000", c4, 12345, 4, store_matrix=False, heaps=True)
+
+    x, p_true, q_true = synth.bernoulli_grid_matrix(4000, 400, seed=3)
+    n_genes, n_genomes = x.shape
+    index, columns = synth.labels_for(n_genes, n_genomes)
+    dense = pd.DataFrame(x, index=index, columns=columns)
+    import time
+    t = time.time()
+    df_opt, res = quiet(ref_pa.compute_bernoulli_grid_core_genome, dense)
+    fit_seconds = time.time() - t
+    ll = ref_pa.__dict__["__bernoulli_grid_loglikelihood__"]
+    grad = ref_pa.__dict__["__bernoulli_grid_loglikelihood_gradient__"]
+    init = df_opt["initial"].values[1:]
+    opt = df_opt["optimum"].values[1:]
+    np.savez_compressed(
+        os.path.join(HERE, "bernoulli_c3_4000x400.npz"),
+        shape=np.asarray(x.shape, dtype=np.int64), x_digest=np.array(hashlib.sha256(x.astype(np.uint8).tobytes()).hexdigest()),
+        fit_initial=df_opt["initial"].values, fit_optimum=df_opt["optimum"].values,
+        fit_x=res.x, fit_fun=np.float64(res.fun), fit_nit=np.int64(res.nit), fit_nfev=np.int64(res.nfev),
+        fit_message=np.array(str(res.message)), fit_seconds=np.float64(fit_seconds),
+        ll_init=np.float64(ll(x, init[:n_genes], init[n_genes:])), grad_init=grad(x, init[:n_genes], init[n_genes:]),
+        ll_opt=np.float64(ll(x, opt[:n_genes], opt[n_genes:])), grad_opt=grad(x, opt[:n_genes], opt[n_genes:]))
+    manifest["bernoulli_c3_4000x400_reference_fit_seconds"] = fit_seconds
+    print("wrote bernoulli_c3_4000x400: init LL", df_opt["initial"].values[0], "opt LL", -res.fun, "nit", res.nit,
+          "nfev", res.nfev, "%.1fs" % fit_seconds)
+
+
 def main():
+    if "--big" in sys.argv:
+        path = os.path.join(HERE, "MANIFEST.json")
+        with open(path) as f:
+            manifest = json.load(f)
+        big_cases(manifest)
+        with open(path, "w") as f:
+            json.dump(manifest, f, indent=1, sort_keys=True)
+        return
     manifest = {
         "numpy": np.__version__, "scipy": scipy.__version__, "pandas": pd.__version__,
         "python": sys.version.split()[0],

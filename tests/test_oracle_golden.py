@@ -5,7 +5,7 @@ import pytest
 import scipy.sparse
 
 import oracle
-from conftest import CURVE_CASES, draw_perms, golden_matrix, load_golden
+from conftest import BIG_CURVE_CASES, CURVE_CASES, draw_perms, golden_matrix, load_golden
 
 
 @pytest.mark.parametrize("name", CURVE_CASES)
@@ -25,6 +25,39 @@ def test_direct_matches_reference(name):
     perms = draw_perms(int(g["seed"]), coo.shape[1], num_iter)
     pan, core = oracle.pan_core_curves_direct(coo, perms)
     assert np.array_equal(np.hstack([pan, core]), g["curves"][:num_iter].astype(np.float64))
+
+
+@pytest.mark.parametrize("name", CURVE_CASES + BIG_CURVE_CASES)
+def test_c_port_matches_reference(name):
+    """oracle/pancore_ref.c -- the checker of the full-size GPU tests and bench.py's CPU arm -- against every
+    curve fixture the live reference produced, directly (not through the numpy oracle)."""
+    import os
+    from oracle import cport
+    g = load_golden(name)
+    coo = golden_matrix(name, g)
+    num_iter = int(g["num_iter"])
+    perms = draw_perms(int(g["seed"]), coo.shape[1], num_iter)
+    pan, core = cport.curves_direct(coo, perms.astype(np.int32), n_threads=min(num_iter, os.cpu_count() or 1))
+    assert pan.dtype == np.float64 and np.array_equal(np.hstack([pan, core]), g["curves"].astype(np.float64))
+    assert np.array_equal(cport.legacy_shuffles(int(g["seed"]), coo.shape[1], min(num_iter, 3)), perms[:3])
+
+
+@pytest.mark.parametrize("name", BIG_CURVE_CASES)
+def test_minrank_matches_reference_at_full_size(name):
+    g = load_golden(name)
+    coo = golden_matrix(name, g)
+    num_iter = min(int(g["num_iter"]), 8)
+    perms = draw_perms(int(g["seed"]), coo.shape[1], num_iter)
+    pan, core = oracle.pan_core_curves_minrank(coo, perms)
+    assert np.array_equal(np.hstack([pan, core]), g["curves"][:num_iter].astype(np.float64))
+
+
+def test_c_port_sums_duplicates_like_the_reference():
+    from oracle import cport
+    g = load_golden("dup_3x4")
+    coo = scipy.sparse.coo_matrix((g["data"], (g["row"], g["col"])), shape=tuple(g["shape"]))
+    pan, core = cport.curves_direct(coo, g["perms"].astype(np.int32))
+    assert np.array_equal(np.hstack([pan, core]), g["curves"].astype(np.float64))
 
 
 def test_stored_perms_are_the_numpy_stream():
@@ -100,3 +133,18 @@ def test_bernoulli_ll_grad():
                                -2.502512292672613, rtol=1e-13)
     np.testing.assert_allclose(oracle.bernoulli_grad(g["kat_x"], g["kat_p"], g["kat_q"]),
                                g["kat_grad"], rtol=1e-13)
+
+
+def test_bernoulli_ll_grad_at_c3_size():
+    """The oracle at config C3's candidate-core size (4,000 x 400) against the live reference's LL and gradient
+    at the reference's own start point and optimum."""
+    import hashlib
+    from pangenomix_b200 import synth
+    g = load_golden("bernoulli_c3_4000x400")
+    x, _, _ = synth.bernoulli_grid_matrix(4000, 400, seed=3)
+    assert hashlib.sha256(x.astype(np.uint8).tobytes()).hexdigest() == str(g["x_digest"])
+    for tag, pq in (("init", g["fit_initial"][1:]), ("opt", g["fit_optimum"][1:])):
+        np.testing.assert_allclose(oracle.bernoulli_ll(x, pq[:4000], pq[4000:]), g["ll_" + tag], rtol=1e-13)
+        np.testing.assert_allclose(oracle.bernoulli_grad(x, pq[:4000], pq[4000:]), g["grad_" + tag], rtol=1e-12)
+    assert float(g["ll_init"]) == float(g["fit_initial"][0])
+    np.testing.assert_allclose(g["ll_opt"], -float(g["fit_fun"]), rtol=1e-15)
