@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define PGX_VERSION 200
+#define PGX_VERSION 300
 
 enum {
     PGX_OK = 0,
@@ -84,6 +84,9 @@ typedef struct pgx_plan {
     int32_t n_superblocks;         /* ceil(n_long / (1024 * slice_words)) */
     int32_t perms_per_cta;         /* 8, 4, 2 or 1: rank tables that share a CTA's shared memory */
     int32_t slice_words;           /* W = 1, 2 or 4: words per lane of a (superblock, genome) line */
+    int32_t max_colsum;            /* max over genomes of d_colsum; 1 .. 65535 lets the kernels count in uint16 bins and
+                                      the host-buffer calls ship uint16 curve steps (0 = unknown: int32 everywhere) */
+    int32_t reserved_i32;
 } pgx_plan;
 
 int pgx_version(void);
@@ -93,9 +96,12 @@ const char *pgx_last_error(void);
 int pgx_device_info(int32_t *sm_count, int32_t *smem_optin_bytes, int64_t *l2_bytes);
 
 /* Pan/core curves for n_perm genome orders (pangenome_analysis.py:81-90).
- *   d_perms  : [n_perm][N] uint16, row i = shuffle_indices of iteration i (:84-85)
+ *   d_perms  : [n_perm][N] uint16, row i = shuffle_indices of iteration i (:84-85).  TRUSTED input: every row
+ *              must be a permutation of 0 .. N-1 (entries >= N are ignored, a genome that does not occur counts
+ *              as never sampled; the host-buffer calls below report such rows as PGX_ERR_INVALID)
  *   d_curves : [n_perm][2N] int32; columns 0..N-1 = pan_genomes[i,:], N..2N-1 =
- *              core_genomes[i,:] (the np.hstack layout of :97).  Overwritten.
+ *              core_genomes[i,:] (the np.hstack layout of :97).  Overwritten; also the kernels' workspace
+ *              (rank rows and histogram rows live in it until the final scan), 16-byte aligned.
  * Asynchronous on ``stream``. */
 int pgx_pan_core_curves(const pgx_plan *plan, const uint16_t *d_perms, int64_t n_perm,
                         int32_t *d_curves, void *stream);
@@ -106,10 +112,14 @@ int pgx_pan_core_curves_f64(const pgx_plan *plan, const uint16_t *d_perms, int64
                             int32_t *d_hist, double *d_curves, void *stream);
 
 /* Host-buffer entry point: h_perms [n_perm][N] uint16 and h_curves [n_perm][2N]
- * (int32 when out_f64 == 0, float64 otherwise) live in host memory (pinned memory makes
- * the copies asynchronous).  The plan stays device-resident.  The call pipelines
- * H2D -> kernels -> D2H over three internal streams in blocks of ``perms_per_block``
- * permutations (0 = choose) and returns when h_curves is complete. */
+ * (int32 when out_f64 == 0, float64 otherwise) live in host memory (pinned h_perms make
+ * the uploads asynchronous).  The plan stays device-resident.  The call pipelines
+ * H2D -> kernels -> D2H -> result over three internal slots in blocks of ``perms_per_block``
+ * permutations (0 = choose) and returns when h_curves is complete.  When plan->max_colsum <= 65535 the
+ * device ships the curves' STEPS as uint16 (half the bytes of int32 curves, a quarter of float64) into pinned
+ * staging owned by the library and host threads rebuild the curves straight into h_curves (PGX_COPY_THREADS).
+ * Rows of h_perms that are not permutations of 0 .. N-1 make the call fail with PGX_ERR_INVALID.
+ * One host-buffer call (this one or pgx_estimate_pan_core) at a time per process. */
 int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int64_t n_perm,
                              void *h_curves, int32_t out_f64, int64_t perms_per_block);
 
@@ -127,10 +137,11 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
  * kernel (1, 2, 4 or 8), row splits per permutation batch and threads per CTA. */
 int pgx_set_tuning(int32_t perms_per_cta, int32_t row_splits, int32_t threads_per_cta);
 
-/* Per-kernel timing for roofline reports: while enabled, every pgx_pan_core_curves*
- * call brackets its list kernel, its bitmap-probe kernel and its scan kernel with CUDA
- * events on the caller's stream.  pgx_profile_read waits for them, returns the summed
- * durations (ms) and the number of calls since the last read, and releases the events. */
+/* Per-kernel timing for roofline reports: while enabled, every pgx_pan_core_curves[_f64]
+ * call brackets its kernels with CUDA events on the caller's stream and runs the two row kernels
+ * back to back.  pgx_profile_read waits for them, returns the summed durations (ms) of the list
+ * kernel, the bitmap-probe kernel and everything else (prep + scan kernels) and the number of
+ * calls since the last read, and releases the events. */
 int pgx_profile_enable(int32_t on);
 int pgx_profile_read(double *list_ms, double *probe_ms, double *scan_ms, int64_t *calls);
 
@@ -222,6 +233,12 @@ int pgx_plan_all_equal_u64(const uint64_t *words, int64_t n, uint64_t value, int
  * anything that is not a complete, well-formed stream of that size; the caller verifies the
  * entry's CRC-32 and falls back to zlib on any error.  Thread-safe (no shared state). */
 int pgx_inflate_raw(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_len);
+
+/* Host half of the compact transfer (no GPU work): rows of 2N uint16 curve steps
+ *   d[0] = pan[0], d[k] = pan[k] - pan[k-1];  d[N] = core[0], d[N+k] = core[k-1] - core[k]
+ * -> curves [n_rows][2N], int32 (out_f64 == 0) or float64.  n_threads 0 = choose. */
+int pgx_expand_deltas(const uint16_t *h_deltas, int64_t n_rows, int32_t n_genomes, void *h_curves,
+                      int32_t out_f64, int32_t n_threads);
 
 /* numpy legacy RandomState stream (host): ``count`` consecutive
  * ``a = np.arange(n); np.random.shuffle(a)`` results as uint16 rows, continuing from the

@@ -21,6 +21,7 @@ EXPORTS = (
     "pgx_heaps_scratch_bytes", "pgx_heaps_fit", "pgx_estimate_pan_core",
     "pgx_plan_bank_order", "pgx_plan_build_bitmap", "pgx_plan_coo_to_csr", "pgx_plan_folded_lists",
     "pgx_plan_missing_genome", "pgx_plan_all_equal_u64", "pgx_plan_balance_rows", "pgx_inflate_raw",
+    "pgx_expand_deltas",
 )
 
 
@@ -49,6 +50,8 @@ class PgxPlan(ctypes.Structure):
         ("n_superblocks", ctypes.c_int32),
         ("perms_per_cta", ctypes.c_int32),
         ("slice_words", ctypes.c_int32),
+        ("max_colsum", ctypes.c_int32),
+        ("reserved_i32", ctypes.c_int32),
     ]
 
 
@@ -103,6 +106,8 @@ def load():
     lib.pgx_plan_all_equal_u64.argtypes = [vp, i64, ctypes.c_uint64, i32]
     lib.pgx_inflate_raw.restype = ctypes.c_int
     lib.pgx_inflate_raw.argtypes = [vp, i64, vp, i64]
+    lib.pgx_expand_deltas.restype = ctypes.c_int
+    lib.pgx_expand_deltas.argtypes = [vp, i64, i32, vp, i32, i32]
     lib.pgx_estimate_pan_core.restype = ctypes.c_int
     lib.pgx_estimate_pan_core.argtypes = [plan_p, vp, ctypes.POINTER(i32), i64, vp, i64]
     lib.pgx_heaps_scratch_bytes.restype = ctypes.c_size_t

@@ -1,0 +1,138 @@
+// Host half of the compact curve transfer of libpgx_b200 (plain C++, no CUDA).
+//
+// A pan/core table row (pangenome_analysis.py:89-90, one permutation) is two monotone curves whose steps are
+// bounded by the gene count of one genome: pan[k] - pan[k-1] = genes first seen in genome perm[k] <= colsum,
+// core[k-1] - core[k] = genes first missed in genome perm[k] <= core[k-1] <= colsum[perm[0]].  Whenever every
+// genome of the table holds at most 65,535 genes the device therefore ships a row as 2N uint16 STEPS
+//   d[0] = pan[0],  d[k] = pan[k] - pan[k-1];   d[N] = core[0],  d[N+k] = core[k-1] - core[k]
+// -- a quarter of the bytes of the float64 row the reference builds (:76-77, :97) and half of an int32 row, over
+// the PCIe link that bounds the host-buffer calls -- and the host threads that have to touch every element of the
+// result anyway (it is fresh pageable memory) rebuild the curves with one prefix sum per half row.
+#include <stdint.h>
+#include <string.h>
+
+#include <algorithm>
+#include <thread>
+#include <vector>
+
+#if defined(__x86_64__)
+#include <immintrin.h>
+#define PGX_X86 1
+#else
+#define PGX_X86 0
+#endif
+
+#include "pgx.h"
+
+namespace pgx {
+int fail(int code, const char *fmt, ...);
+
+namespace {
+
+template <typename OutT>
+void expand_row_scalar(const uint16_t *d, long long n, OutT *out)
+{
+    int32_t run = 0;
+    for (long long k = 0; k < n; ++k) {
+        run += d[k];
+        out[k] = static_cast<OutT>(run);
+    }
+    run = d[n];
+    out[n] = static_cast<OutT>(run);
+    for (long long k = 1; k < n; ++k) {
+        run -= d[n + k];
+        out[n + k] = static_cast<OutT>(run);
+    }
+}
+
+#if PGX_X86
+// inclusive prefix sum of 8 int32 lanes
+__attribute__((target("avx2"))) inline __m256i scan8(__m256i v)
+{
+    v = _mm256_add_epi32(v, _mm256_slli_si256(v, 4));
+    v = _mm256_add_epi32(v, _mm256_slli_si256(v, 8));                       // inclusive inside each 128-bit half
+    const __m256i low_total = _mm256_permutevar8x32_epi32(v, _mm256_set1_epi32(3));
+    return _mm256_add_epi32(v, _mm256_blend_epi32(_mm256_setzero_si256(), low_total, 0xf0));
+}
+
+__attribute__((target("avx2"))) inline void store8(int32_t *out, __m256i v)
+{
+    _mm256_storeu_si256(reinterpret_cast<__m256i *>(out), v);
+}
+
+__attribute__((target("avx2"))) inline void store8(double *out, __m256i v)
+{
+    _mm256_storeu_pd(out, _mm256_cvtepi32_pd(_mm256_castsi256_si128(v)));
+    _mm256_storeu_pd(out + 4, _mm256_cvtepi32_pd(_mm256_extracti128_si256(v, 1)));
+}
+
+// out[k] = base + sign * (d[0] + ... + d[k]) for k < count
+template <typename OutT>
+__attribute__((target("avx2"))) void prefix_avx2(const uint16_t *d, long long count, int32_t base, bool subtract, OutT *out)
+{
+    __m256i carry = _mm256_set1_epi32(base);
+    long long k = 0;
+    for (; k + 8 <= count; k += 8) {
+        __m256i v = _mm256_cvtepu16_epi32(_mm_loadu_si128(reinterpret_cast<const __m128i *>(d + k)));
+        v = scan8(v);
+        v = subtract ? _mm256_sub_epi32(carry, v) : _mm256_add_epi32(carry, v);
+        store8(out + k, v);
+        carry = _mm256_permutevar8x32_epi32(v, _mm256_set1_epi32(7));
+    }
+    int32_t run = _mm256_extract_epi32(carry, 0);
+    for (; k < count; ++k) {
+        run = subtract ? run - d[k] : run + d[k];
+        out[k] = static_cast<OutT>(run);
+    }
+}
+
+template <typename OutT>
+__attribute__((target("avx2"))) void expand_row_avx2(const uint16_t *d, long long n, OutT *out)
+{
+    prefix_avx2<OutT>(d, n, 0, false, out);
+    out[n] = static_cast<OutT>(d[n]);
+    if (n > 1) prefix_avx2<OutT>(d + n + 1, n - 1, d[n], true, out + n + 1);
+}
+#endif
+
+template <typename OutT>
+void expand_rows(const uint16_t *deltas, long long r0, long long r1, long long n, OutT *out)
+{
+#if PGX_X86
+    static const bool avx2 = __builtin_cpu_supports("avx2");
+    if (avx2) {
+        for (long long r = r0; r < r1; ++r) expand_row_avx2<OutT>(deltas + r * 2 * n, n, out + r * 2 * n);
+        return;
+    }
+#endif
+    for (long long r = r0; r < r1; ++r) expand_row_scalar<OutT>(deltas + r * 2 * n, n, out + r * 2 * n);
+}
+
+}  // namespace
+
+// Rows [r0, r1) of a block of step rows -> curves (int32 or float64), on the calling thread.
+void expand_delta_rows(const uint16_t *deltas, long long r0, long long r1, long long n, void *out, bool out_f64)
+{
+    if (out_f64) expand_rows<double>(deltas, r0, r1, n, static_cast<double *>(out));
+    else expand_rows<int32_t>(deltas, r0, r1, n, static_cast<int32_t *>(out));
+}
+
+}  // namespace pgx
+
+extern "C" int pgx_expand_deltas(const uint16_t *h_deltas, int64_t n_rows, int32_t n_genomes, void *h_curves,
+                                 int32_t out_f64, int32_t n_threads)
+{
+    if (n_rows < 0 || n_genomes < 1) return pgx::fail(PGX_ERR_INVALID, "bad shape passed to pgx_expand_deltas");
+    if (n_rows == 0) return PGX_OK;
+    if (!h_deltas || !h_curves) return pgx::fail(PGX_ERR_INVALID, "null pointer passed to pgx_expand_deltas");
+    int threads = n_threads > 0 ? n_threads : static_cast<int>(std::min(8u, std::max(1u, std::thread::hardware_concurrency())));
+    threads = static_cast<int>(std::max<long long>(1, std::min<long long>(threads, n_rows * n_genomes / 65536)));
+    std::vector<std::thread> pool;
+    for (int t = 1; t < threads; ++t)
+        pool.emplace_back([=]() {
+            pgx::expand_delta_rows(h_deltas, n_rows * t / threads, n_rows * (t + 1) / threads, n_genomes, h_curves, out_f64 != 0);
+        });
+    pgx::expand_delta_rows(h_deltas, 0, n_rows / threads, n_genomes, h_curves, out_f64 != 0);
+    for (auto &th : pool) th.join();
+    return PGX_OK;
+}

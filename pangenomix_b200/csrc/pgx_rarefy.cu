@@ -11,21 +11,34 @@
 // of both histograms is a column sum of the table (closed form); the row kernels only ever
 // produce the ONE non-zero statistic of every (gene, permutation).
 //
+// Kernel 0 (prep_kernel): one CTA per permutation.  Inverts the genome order into a rank row
+//   (uint16, scattered through shared memory, written out coalesced) and writes the closed-form
+//   gene classes (empty, universal, single-genome, single-absence genes; bin 0) into the histogram
+//   row, which therefore needs no memset and the scan no table look-ups.
 // Kernel 1 (list_kernel<B>): genes with a short list.  Persistent CTAs; per item a CTA stages the
-//   rank tables of B permutations in shared memory as T[genome][B] uint16 -- one 16-byte line
-//   per genome for B = 8 -- and its warps stream runs of sub-blocks of 32 rows, one lane per row,
-//   4 chunk loads in flight.  Every index costs ONE shared-memory gather that serves all B
-//   permutations, folded into packed uint16x2 running minima (VIMNMX.U16x2).  The host ordered
-//   the indices of a row so that the lanes of a wavefront hit distinct banks.  If the min is 0
-//   the wanted statistic is the mex of the list's ranks instead: such (row, permutation) events
-//   are queued per warp and resolved 32 at a time against the sorted copy of the lists.
+//   rank rows of B permutations in shared memory as T[genome][B] uint16 -- one 16-byte line
+//   per genome for B = 8, one conflict-free 16-byte store per genome -- and its warps stream runs
+//   of sub-blocks of 32 rows, one lane per row, three chunk loads in flight.  Every index costs
+//   ONE shared-memory gather that serves all B permutations, folded into packed uint16x2 running
+//   minima (VIMNMX.U16x2).  The host ordered the indices of a row so that the lanes of a
+//   wavefront hit distinct banks.  If the min is 0 the wanted statistic is the mex of the list's
+//   ranks instead: such (row, permutation) events are queued per warp and resolved 32 at a time
+//   against the sorted copy of the lists.
 // Kernel 2 (probe_kernel<W>): genes with long lists, stored as a genome-major, bit-sliced
 //   bitmap (32 genes per word).  A warp walks one genome order for 1,024 W genes at once, one
 //   coalesced line of 128 W bytes per step; the first genome whose bit differs from the rank-0
 //   genome's bit is the gene's statistic.  O(N / m) steps instead of O(m) gathers.  It runs
 //   beside kernel 1 on a second stream (shared-memory-pipe bound vs issue bound).
-// Kernel 3 (scan_kernel): adds the closed-form gene classes and turns each histogram into
-//   its curve with a block-wide prefix scan, in place.
+// Kernel 3 (scan_kernel): turns each histogram row into its two curves with block-wide prefix scans.
+//
+// Histogram bins are uint16 pairs packed in 32-bit words ("P16") whenever every genome of the table
+// holds at most 65,535 genes (plan.max_colsum): a bin counts genes that first appear in, or first go
+// missing at, ONE genome, so it cannot exceed that genome's gene count (pan side) or the first genome's
+// (core side), and a 32-bit atomic add of 1 or 1 << 16 never carries.  The packed row is half the size
+// of the int32 output row: it lives in the upper half of the caller's output row, the rank row in the
+// lower half, and the scan expands in place.  The host-buffer calls skip the scan altogether and ship
+// the packed rows -- the curves' STEPS -- to the host, which rebuilds the curves while it fills the
+// caller's result (pgx_expand.cpp).  Tables with a larger genome fall back to int32 bins.
 // Host entry points at the end of the file: the device-pointer calls, the host-buffer pipeline
 // (pgx_pan_core_curves_host) and the reference's whole loop in one call (pgx_estimate_pan_core).
 #include <stdlib.h>
@@ -35,7 +48,6 @@
 
 #include <atomic>
 #include <chrono>
-#include <condition_variable>
 #include <mutex>
 #include <thread>
 #include <vector>
@@ -44,11 +56,13 @@
 
 namespace pgx {
 
+void expand_delta_rows(const uint16_t *deltas, long long r0, long long r1, long long n, void *out, bool out_f64);
+
 namespace {
 
 constexpr int SENTINELS = 32;          // rank-table rows N .. N+31 hold 0xffff (plan.py)
 // Optional CUDA-event brackets around the kernels of every call (bench.py's roofline).
-struct ProfileEvents { cudaEvent_t begin, list_done, probe_done, end; };
+struct ProfileEvents { cudaEvent_t begin, prep_done, list_done, probe_done, end; };
 bool g_profile_on = false;
 std::mutex g_profile_mu;
 std::vector<ProfileEvents> g_profile_events;
@@ -60,7 +74,84 @@ struct Tuning {
 };
 Tuning g_tuning;
 const bool g_no_overlap = getenv("PGX_NO_OVERLAP") != nullptr;
+const bool g_wide_bins = getenv("PGX_WIDE_BINS") != nullptr;      // force int32 histogram bins (tests, A/B)
 
+// Where the kernels of one call keep their per-permutation rows.
+//   hist  : histogram row of permutation p at hist + p * hist_stride (32-bit words); 2N int32 bins
+//           (pan | core) or, packed, N words of uint16 pairs (bin i of the 2N in half (i & 1) of word i >> 1)
+//   ranks : rank row (uint16 [N]) of permutation p at ranks + p * rank_stride (uint16 units)
+struct Work {
+    uint32_t *hist;
+    long long hist_stride;
+    uint16_t *ranks;
+    long long rank_stride;
+};
+
+// bin ``idx`` (0 .. 2N-1: pan bins then core bins) of a histogram row += v
+template <bool P16>
+__device__ __forceinline__ void hist_add(uint32_t *row, int idx, uint32_t v)
+{
+    if constexpr (P16) atomicAdd(row + (idx >> 1), v << ((idx & 1) * 16));
+    else atomicAdd(row + idx, v);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 0: rank rows + closed forms
+// ---------------------------------------------------------------------------------------------
+// Closed forms (every gene that never reaches a row kernel).  Bin 0 of both sides is the number of genes the
+// first genome holds (pan[0] = core[0]).  A gene living in a single genome c has first presence rank[c] and
+// first absence 1 if c comes first, 0 otherwise; a gene missing from a single genome c the mirror image.
+// int32 bins hold the core side as "genes lost so far" (bin 0 = G - colsum[first]); packed bins hold the
+// curve's steps (bin 0 = core[0] = colsum[first]), because G - colsum may not fit 16 bits.
+template <bool P16>
+__global__ void __launch_bounds__(256)
+prep_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const Work work, int *__restrict__ bad_rows)
+{
+    extern __shared__ __align__(16) uint16_t s_rank[];   // [N]
+    const int n = plan.n_genomes;
+    const long long p = blockIdx.x;
+    const uint16_t *__restrict__ perm = perms + p * n;
+    const int tid = threadIdx.x;
+
+    for (int g = tid; g < n; g += blockDim.x) s_rank[g] = 0xffffu;
+    __syncthreads();
+    for (int k = tid; k < n; k += blockDim.x) {
+        const uint32_t g = perm[k];
+        if (g < static_cast<uint32_t>(n)) s_rank[g] = static_cast<uint16_t>(k);
+    }
+    __syncthreads();
+    uint16_t *__restrict__ ranks = work.ranks + p * work.rank_stride;
+    bool missing = false;
+    for (int g = tid; g < n; g += blockDim.x) {
+        const uint16_t r = s_rank[g];
+        missing |= r == 0xffffu;
+        ranks[g] = r;
+    }
+    // a row that is not a permutation of 0 .. N-1 leaves a genome without a rank
+    if (missing && bad_rows) atomicAdd(bad_rows, 1);
+
+    const uint32_t first = min(static_cast<uint32_t>(perm[0]), static_cast<uint32_t>(n - 1));
+    const int col_first = plan.d_colsum[first];
+    auto bin = [&](int idx) -> uint32_t {            // idx in [0, 2N)
+        const int side = idx >= n;
+        const int k = idx - side * n;
+        if (k == 0) return static_cast<uint32_t>(P16 || side == 0 ? col_first : plan.n_genes - col_first);
+        const int32_t *w_list = side == 0 ? plan.d_w_present : plan.d_w_absent;
+        const int32_t *w_other = side == 0 ? plan.d_w_absent : plan.d_w_present;
+        const uint32_t g = min(static_cast<uint32_t>(perm[k]), static_cast<uint32_t>(n - 1));
+        return static_cast<uint32_t>(w_list[g] + (k == 1 ? w_other[first] : 0));
+    };
+    uint32_t *__restrict__ hist = work.hist + p * work.hist_stride;
+    if constexpr (P16) {
+        for (int w = tid; w < n; w += blockDim.x) hist[w] = bin(2 * w) | (bin(2 * w + 1) << 16);
+    } else {
+        for (int i = tid; i < 2 * n; i += blockDim.x) hist[i] = bin(i);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// Kernel 1: list rows
+// ---------------------------------------------------------------------------------------------
 template <int B>
 struct Packed {
     static constexpr int REGS = (B + 1) / 2;
@@ -123,15 +214,17 @@ __device__ __noinline__ int mex_probe(const uint16_t *__restrict__ perm,
 
 // Deferred mex events of a warp: (list row << 4 | absent_list << 3 | permutation slot).
 constexpr int EVENT_QUEUE = 64;
-constexpr int LIST_DEPTH = 4;           // chunk loads in flight per lane
 
-// 48 registers x 1,024 threads leave a quarter of the register file to the probe kernel's CTAs,
-// which run beside this one on a second stream (the list kernel is bound by the shared-memory
-// pipe, the probe kernel by instruction issue).
-template <int B>
-__global__ void __maxnreg__(48)
+// The chunk stream of a task is prefetched through THREE separately named buffers, each refilled by its own
+// load instruction: a rotating buffer refilled by ONE static LDG gets one scoreboard from the compiler, and waiting
+// for its oldest chunk then waits for every chunk load in flight (decoded from the SASS control bits of round 1's
+// kernel).  The end of a sub-block issues its B histogram updates back to back; the rare "min == 0" events are
+// collected in a per-lane mask and queued under one vote.  REGCAP x threads is sized so that CTAs of the probe
+// kernel, which runs beside this one on a second stream, find registers on every SM (48 x 1,024 or 64 x 768).
+template <int B, int REGCAP, bool P16>
+__global__ void __maxnreg__(REGCAP)
 list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long long n_perm,
-            int32_t *__restrict__ hist, const int splits, const long long n_items)
+            const Work work, const int splits, const long long n_items)
 {
     extern __shared__ __align__(16) uint16_t table[];   // [(N + 32)][B], then the warps' event queues
     __shared__ int s_next_task;
@@ -144,7 +237,6 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
                       (tid >> 5) * EVENT_QUEUE;
     const uint4 *__restrict__ chunks = reinterpret_cast<const uint4 *>(plan.d_chunks);
     const int4 *__restrict__ tasks = reinterpret_cast<const int4 *>(plan.d_tasks);
-    const long long row_stride = 2ll * n;
 
     // Persistent CTAs: item = (batch of B permutations, share ``split`` of the tasks).  The whole
     // grid is resident at once, so CTAs of the probe kernel can fill the rest of every SM.
@@ -156,15 +248,26 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
     const int split = static_cast<int>(item / batches);
     const int n_valid = static_cast<int>(min(static_cast<long long>(B), n_perm - p0));
 
-    // ---- stage the inverse permutations: T[perm[k]][q] = k (B independent loads in flight) ----
-    for (int k = tid; k < n; k += blockDim.x) {
-        uint32_t g[B];
+    // ---- stage the rank rows: T[g][q] = rank of genome g under permutation p0 + q (B coalesced loads, one store) ----
+    {
+        const uint16_t *__restrict__ ranks = work.ranks + p0 * work.rank_stride;
+        for (int g = tid; g < n + SENTINELS; g += blockDim.x) {
+            uint32_t r[B];
 #pragma unroll
-        for (int q = 0; q < B; ++q) g[q] = q < n_valid ? perms[(p0 + q) * n + k] : static_cast<uint32_t>(k);
-#pragma unroll
-        for (int q = 0; q < B; ++q) table[g[q] * B + q] = q < n_valid ? static_cast<uint16_t>(k) : static_cast<uint16_t>(0xffffu);
+            for (int q = 0; q < B; ++q)
+                r[q] = (q < n_valid && g < n) ? static_cast<uint32_t>(ranks[q * work.rank_stride + g]) : 0xffffu;   // sentinels never win a min
+            if constexpr (B == 8) {
+                *reinterpret_cast<uint4 *>(table + g * 8) =
+                    make_uint4(r[0] | (r[1] << 16), r[2] | (r[3] << 16), r[4] | (r[5] << 16), r[6] | (r[7] << 16));
+            } else if constexpr (B == 4) {
+                *reinterpret_cast<uint2 *>(table + g * 4) = make_uint2(r[0] | (r[1] << 16), r[2] | (r[3] << 16));
+            } else if constexpr (B == 2) {
+                *reinterpret_cast<uint32_t *>(table + g * 2) = r[0] | (r[1] << 16);
+            } else {
+                table[g] = static_cast<uint16_t>(r[0]);
+            }
+        }
     }
-    for (int k = tid; k < SENTINELS * B; k += blockDim.x) table[n * B + k] = 0xffffu;   // never win a min
     if (tid == 0) s_next_task = 0;
     __syncthreads();
 
@@ -184,13 +287,12 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
         const int s0 = plan.d_sorted_ptr[row];
         const int k = mex_probe(perms + (p0 + q) * n, plan.d_sorted_idx + s0, plan.d_sorted_ptr[row + 1] - s0, n);
         // present list: min -> pan histogram, mex -> core histogram; absent list: swapped.
-        if (k < n) atomicAdd(hist + (p0 + q) * row_stride + ((ev & 8) ? 0 : n) + k, 1);
+        if (k < n) hist_add<P16>(work.hist + (p0 + q) * work.hist_stride, ((ev & 8) ? 0 : n) + k, 1u);
     };
 
     // A task is a run of consecutive sub-blocks (32 rows x nch chunks each) laid out back to
-    // back, so the warp streams chunk iterations 0 .. n_sub * nch - 1 with LIST_DEPTH loads in
-    // flight and closes a sub-block every nch iterations.  The next task's descriptor is
-    // fetched while the current one streams.
+    // back, so the warp streams chunk iterations 0 .. n_sub * nch - 1 and closes a sub-block every
+    // nch iterations.  The next task's descriptor is fetched while the current one streams.
     int4 td = next_task();
     while (td.y & 0xffff) {
         const int4 td_next = next_task();
@@ -201,53 +303,54 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
         const uint4 *cp = chunks + td.x + lane;
         PGX_DEVICE_CHECK(td.x >= 0 && static_cast<long long>(td.x) + static_cast<long long>(total) * 32 <= plan.n_chunks);
         PGX_DEVICE_CHECK(td.z >= 0 && td.z + n_rows <= plan.n_rows);
-        int32_t *list_hist = hist + (absent_list ? n : 0);
-
-        uint4 buf[LIST_DEPTH];
-#pragma unroll
-        for (int d = 0; d < LIST_DEPTH; ++d) buf[d] = d < total ? ldg_stream(cp + d * 32) : make_uint4(0, 0, 0, 0);
+        uint32_t *list_hist = work.hist + p0 * work.hist_stride;
+        const int side = absent_list ? n : 0;
 
         uint32_t acc[REGS];
 #pragma unroll
         for (int i = 0; i < REGS; ++i) acc[i] = 0xffffffffu;
         int left = nch, row = td.z + lane, rows_left = n_rows - lane;
-        for (int s = 0; s < total; ++s) {
-            const uint4 cur = buf[0];
-#pragma unroll
-            for (int d = 0; d + 1 < LIST_DEPTH; ++d) buf[d] = buf[d + 1];
-            if (s + LIST_DEPTH < total) buf[LIST_DEPTH - 1] = ldg_stream(cp + (s + LIST_DEPTH) * 32);
+
+        // one chunk iteration: 8 gathers; every nch-th iteration closes a sub-block of 32 rows
+        auto consume = [&](const uint4 cur) {
             PGX_DEVICE_CHECK((cur.x & 0xffffu) < static_cast<uint32_t>(n + SENTINELS) && (cur.x >> 16) < static_cast<uint32_t>(n + SENTINELS) &&
                              (cur.y & 0xffffu) < static_cast<uint32_t>(n + SENTINELS) && (cur.y >> 16) < static_cast<uint32_t>(n + SENTINELS) &&
                              (cur.z & 0xffffu) < static_cast<uint32_t>(n + SENTINELS) && (cur.z >> 16) < static_cast<uint32_t>(n + SENTINELS) &&
                              (cur.w & 0xffffu) < static_cast<uint32_t>(n + SENTINELS) && (cur.w >> 16) < static_cast<uint32_t>(n + SENTINELS));
             gather_chunk<B>(table, cur, acc);
-            if (--left) continue;
-
-            // ---- a sub-block is complete: one statistic per (row, permutation) ----
+            if (--left) return;
             const bool valid = rows_left > 0;
+            uint32_t zero = 0;                            // bit q: this row's min under permutation q is 0
 #pragma unroll
             for (int q = 0; q < B; ++q) {
                 if (q < n_valid) {
                     uint32_t mn;
                     if constexpr (B == 1) mn = acc[0] & 0xffffu;
                     else mn = (acc[q >> 1] >> ((q & 1) * 16)) & 0xffffu;
-                    PGX_DEVICE_CHECK(!valid || mn < static_cast<uint32_t>(n));          // a real row always holds a genome
-                    if (valid && mn != 0) atomicAdd(list_hist + (p0 + q) * row_stride + mn, 1);
-                    // min == 0: the wanted statistic is the mex; queue it, resolve 32 at a time
-                    const bool ev = valid && mn == 0;
+                    if (valid) {
+                        // (mn >= n: a rank row with a hole, i.e. not a permutation -- counted nowhere, reported by the host calls)
+                        if (mn == 0) zero |= 1u << q;
+                        else if (mn < static_cast<uint32_t>(n)) hist_add<P16>(list_hist + q * work.hist_stride, side + static_cast<int>(mn), 1u);
+                    }
+                }
+            }
+            // min == 0: the wanted statistic is the mex; queue (row, permutation), resolve 32 at a time
+            if (__any_sync(FULL_MASK, zero != 0)) {
+#pragma unroll 1
+                for (int q = 0; q < B; ++q) {
+                    const bool ev = (zero >> q) & 1u;
                     const uint32_t m = __ballot_sync(FULL_MASK, ev);
-                    if (m) {
-                        PGX_DEVICE_CHECK(queued + __popc(m) <= EVENT_QUEUE);
+                    if (!m) continue;
+                    PGX_DEVICE_CHECK(queued + __popc(m) <= EVENT_QUEUE);
                     if (ev) queue[queued + __popc(m & ((1u << lane) - 1u))] =
-                            (static_cast<uint32_t>(row) << 4) | (absent_list << 3) | q;
-                        queued += __popc(m);
+                            (static_cast<uint32_t>(row) << 4) | (absent_list << 3) | static_cast<uint32_t>(q);
+                    queued += __popc(m);
+                    __syncwarp();
+                    if (queued >= 32) {
+                        queued -= 32;
+                        const uint32_t e = queue[queued + lane];
                         __syncwarp();
-                        if (queued >= 32) {
-                            queued -= 32;
-                            const uint32_t e = queue[queued + lane];
-                            __syncwarp();
-                            resolve(e);
-                        }
+                        resolve(e);
                     }
                 }
             }
@@ -256,6 +359,25 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
             left = nch;
             row += 32;
             rows_left -= 32;
+        };
+
+        uint4 b0 = total > 0 ? ldg_stream(cp) : make_uint4(0, 0, 0, 0);
+        uint4 b1 = total > 1 ? ldg_stream(cp + 32) : make_uint4(0, 0, 0, 0);
+        uint4 b2 = total > 2 ? ldg_stream(cp + 64) : make_uint4(0, 0, 0, 0);
+        for (int s = 0; s < total; s += 3) {
+            const uint4 c0 = b0;
+            if (s + 3 < total) b0 = ldg_stream(cp + (s + 3) * 32);
+            consume(c0);
+            if (s + 1 < total) {
+                const uint4 c1 = b1;
+                if (s + 4 < total) b1 = ldg_stream(cp + (s + 4) * 32);
+                consume(c1);
+            }
+            if (s + 2 < total) {
+                const uint4 c2 = b2;
+                if (s + 5 < total) b2 = ldg_stream(cp + (s + 5) * 32);
+                consume(c2);
+            }
         }
         td = td_next;
     }
@@ -264,7 +386,10 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
     }
 }
 
-// Bitmap rows, bit-sliced: 32 genes per word, genome-major.  A warp owns one superblock of
+// ---------------------------------------------------------------------------------------------
+// Kernel 2: bitmap rows
+// ---------------------------------------------------------------------------------------------
+// Bit-sliced: 32 genes per word, genome-major.  A warp owns one superblock of
 // 1,024 W bitmap rows (W = 1, 2 or 4 words per lane) and one permutation; lane l holds rows
 // 32 W l .. 32 W l + 32 W - 1 of the superblock as W words.  Walking the genome order, step k
 // loads ONE coalesced line of 128 W bytes -- the presence bits of all 1,024 W genes in genome
@@ -302,10 +427,17 @@ __device__ __forceinline__ void load_line(const uint32_t *p, uint32_t (&w)[W])
     }
 }
 
-template <int W>
+// Late in a walk a handful of genes keep the whole warp loading 128 W-byte lines.  From STRAGGLER_MIN_RANK on,
+// once at most ``straggler_max`` genes are pending, the warp finishes them one by one instead: 32 lanes test 32
+// consecutive ranks of ONE gene (a 4-byte load each), the first differing lane is the gene's statistic.  Each
+// such scan is a chain of dependent loads, so the hand-over pays only for the last few genes (measured on C4:
+// probe kernel 2.39 ms without, 2.13 ms from 16 genes, 2.33 ms from 64, 4.4 ms from 128).
+constexpr int STRAGGLER_MIN_RANK = 64;
+
+template <int W, bool P16>
 __global__ void __launch_bounds__(SLICE_WARPS * 32, 8)
 probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long long n_perm,
-             int32_t *__restrict__ hist)
+             const Work work, const int straggler_max)
 {
     constexpr int DEPTH = W == 4 ? 4 : 8;          // lines in flight per warp
     const int n = plan.n_genomes;
@@ -316,7 +448,8 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
 
     const uint32_t *__restrict__ lines = plan.d_bits + (static_cast<size_t>(sb) * n) * (32 * W) + lane * W;
     const uint16_t *__restrict__ perm = perms + q * n;
-    int32_t *out = hist + q * 2ll * n + (lane == 1 ? n : 0);      // lane 0 adds pan counts, lane 1 core counts
+    uint32_t *hist_q = work.hist + q * work.hist_stride;
+    const int my_side = lane == 1 ? n : 0;                        // lane 0 adds pan counts, lane 1 core counts
 
     uint32_t pending[W], b0[W];
 #pragma unroll
@@ -324,12 +457,53 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
         const long long left = static_cast<long long>(plan.n_long) - (sb * (1024 * W) + (lane * W + j) * 32);
         pending[j] = left >= 32 ? 0xffffffffu : (left <= 0 ? 0u : ((1u << left) - 1u));
     }
-    const uint32_t genome0 = perm[0];
+    // (genome indices are clamped: a row that is not a permutation must not read outside the bitmap)
+    const uint32_t last = static_cast<uint32_t>(n - 1);
+    const uint32_t genome0 = min(static_cast<uint32_t>(perm[0]), last);
     load_line<W>(lines + static_cast<size_t>(genome0) * (32 * W), b0);
 
     for (int k0 = 0; k0 < n; k0 += 32) {
         // genomes of ranks k0 .. k0 + 31; ranks past the end repeat the rank-0 genome (never a flip)
-        const uint32_t chunk = k0 + lane < n ? perm[k0 + lane] : genome0;
+        const uint32_t chunk = k0 + lane < n ? min(static_cast<uint32_t>(perm[k0 + lane]), last) : genome0;
+        if (k0 >= STRAGGLER_MIN_RANK && straggler_max > 0) {
+            uint32_t cnt = 0;
+#pragma unroll
+            for (int x = 0; x < W; ++x) cnt += __popc(pending[x]);
+            if (__reduce_add_sync(FULL_MASK, cnt) <= static_cast<uint32_t>(straggler_max)) {
+                // all ranks below k0 have been walked; every pending gene flips at some rank >= k0
+                const uint32_t *__restrict__ column = plan.d_bits + (static_cast<size_t>(sb) * n) * (32 * W);
+#pragma unroll
+                for (int x = 0; x < W; ++x) {
+                    uint32_t owners = __ballot_sync(FULL_MASK, pending[x] != 0);
+                    while (owners) {
+                        const int src = __ffs(owners) - 1;
+                        owners &= owners - 1;
+                        uint32_t word = __shfl_sync(FULL_MASK, pending[x], src);
+                        const uint32_t first = __shfl_sync(FULL_MASK, b0[x], src);
+                        const uint32_t *__restrict__ cell = column + src * W + x;
+                        while (word) {
+                            const int bit = __ffs(word) - 1;
+                            word &= word - 1;
+                            const uint32_t want = (first >> bit) & 1u;
+                            uint32_t c = chunk;                       // ranks k0 .. k0 + 31 first
+                            int k = k0;
+                            while (k < n) {                           // (a bitmap row always flips: the bound only guards a corrupt plan)
+                                const uint32_t v = __ldg(cell + static_cast<size_t>(c) * (32 * W));
+                                const uint32_t differs = __ballot_sync(FULL_MASK, ((v >> bit) & 1u) != want);
+                                if (differs) {
+                                    // rank-0 bit 0: first presence (pan side); rank-0 bit 1: first absence (core side)
+                                    if (lane == 0) hist_add<P16>(hist_q, (want ? n : 0) + k + __ffs(differs) - 1, 1u);
+                                    break;
+                                }
+                                k += 32;
+                                c = k + lane < n ? min(static_cast<uint32_t>(perm[k + lane]), last) : genome0;
+                            }
+                        }
+                    }
+                }
+                return;
+            }
+        }
 #pragma unroll 1
         for (int j0 = 0; j0 < 32; j0 += DEPTH) {
             uint32_t d[DEPTH][W];
@@ -366,7 +540,7 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
                 const uint32_t total = __reduce_add_sync(FULL_MASK, packed);     // <= 4,096 per half
                 const uint32_t mine = lane == 1 ? total >> 16 : total & 0xffffu;
                 PGX_DEVICE_CHECK(k0 + j0 + j > 0 && k0 + j0 + j < n);
-                if (lane < 2 && mine) atomicAdd(out + (k0 + j0 + j), static_cast<int>(mine));
+                if (lane < 2 && mine) hist_add<P16>(hist_q, my_side + k0 + j0 + j, mine);
             }
             uint32_t left = 0;
 #pragma unroll
@@ -377,166 +551,120 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
     PGX_DEVICE_CHECK(false && "a bitmap row never flipped: it is empty or universal and must not be in the bitmap");
 }
 
-// Histogram -> curve, in place when OutT == int32_t and out == hist.
-template <typename OutT>
+// ---------------------------------------------------------------------------------------------
+// Kernel 3: histogram rows -> curves
+// ---------------------------------------------------------------------------------------------
+// One CTA per permutation: the pan half, then the core half, 2,048 bins per step with 16-byte accesses when the
+// genome count allows (VEC: N % 8 == 0).  The output row may BE the buffer the histogram row lives in:
+//   int32 bins:  out == hist, every bin is replaced by its curve value;
+//   packed bins: the histogram sits in the upper half of the int32 output row (bytes [4N, 8N) of 8N).  The pan half
+//                writes bytes [0, 4N) only; the core half reads bin k at byte 6N + 2k and writes curve value k at
+//                byte 4N + 4k, which stays behind every bin still to be read while k < N; all loads of a step
+//                precede its stores (the block-wide barrier of the scan), and the pan bins are dead by then.
+template <typename OutT, bool P16, bool VEC>
 __global__ void __launch_bounds__(256)
-scan_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const int32_t *hist, OutT *out)
-{
-    constexpr int ITEMS = 4;
-    constexpr int THREADS = 256;
-    __shared__ int warp_tot[THREADS / 32];
-
-    const int n = plan.n_genomes;
-    const long long p = blockIdx.x;
-    const int side = blockIdx.y;   // 0 = pan, 1 = core
-    const int32_t *h = hist + p * 2ll * n + static_cast<long long>(side) * n;
-    OutT *o = out + p * 2ll * n + static_cast<long long>(side) * n;
-    const uint16_t *perm = perms + p * n;
-    // Closed forms.  Bin 0: genes present in (pan) / absent from (core) the first genome.
-    // Genes living in / missing from a single genome c: the list-side statistic is rank[c];
-    // the other one is 1 if c comes first and 0 otherwise.
-    const int32_t *w_list = side == 0 ? plan.d_w_present : plan.d_w_absent;
-    const int32_t *w_other = side == 0 ? plan.d_w_absent : plan.d_w_present;
-    const int first = perm[0];
-    const int col_first = plan.d_colsum[first];
-    const int bin0 = side == 0 ? col_first : plan.n_genes - col_first;
-    const int add1 = w_other[first];
-
-    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int carry = 0;
-    for (int base = 0; base < n; base += THREADS * ITEMS) {
-        int v[ITEMS];
-        int run = 0;
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const int k = base + tid * ITEMS + i;
-            int x = 0;
-            if (k < n) {
-                if (k == 0) x = bin0;
-                else x = h[k] + w_list[perm[k]] + (k == 1 ? add1 : 0);
-            }
-            run += x;
-            v[i] = run;
-        }
-        int incl = run;
-#pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int y = __shfl_up_sync(FULL_MASK, incl, off);
-            if (lane >= off) incl += y;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        int before = 0, total = 0;
-#pragma unroll
-        for (int i = 0; i < THREADS / 32; ++i) {
-            const int wt = warp_tot[i];
-            if (i < warp) before += wt;
-            total += wt;
-        }
-        const int excl = carry + before + incl - run;
-#pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            const int k = base + tid * ITEMS + i;
-            if (k < n) {
-                const int c = excl + v[i];
-                o[k] = static_cast<OutT>(side == 0 ? c : plan.n_genes - c);
-            }
-        }
-        carry += total;
-        __syncthreads();
-    }
-}
-
-// EXPERIMENT, off unless PGX_SCAN_V8=1: the same scan with 16-byte loads and stores, 8 bins per thread, for
-// tables whose genome count is a multiple of 8.  Measured on C4: 0.523 -> 0.422 ms per 10,000 permutations; six
-// parity tests passed with it, the whole -m gpu suite has not run under it yet (scripts/r02_first.sh does that).
-template <typename OutT>
-__global__ void __launch_bounds__(256)
-scan_kernel_v8(const pgx_plan plan, const uint16_t *__restrict__ perms, const int32_t *hist, OutT *out)
+scan_kernel(const pgx_plan plan, const Work work, OutT *out)
 {
     constexpr int ITEMS = 8;
     constexpr int THREADS = 256;
     __shared__ int warp_tot[THREADS / 32];
 
-    const int n = plan.n_genomes;                    // n % 8 == 0 (checked by the launcher)
+    const int n = plan.n_genomes;
     const long long p = blockIdx.x;
-    const int side = blockIdx.y;
-    const int32_t *h = hist + p * 2ll * n + static_cast<long long>(side) * n;
-    OutT *o = out + p * 2ll * n + static_cast<long long>(side) * n;
-    const uint16_t *perm = perms + p * n;
-    const int32_t *w_list = side == 0 ? plan.d_w_present : plan.d_w_absent;
-    const int32_t *w_other = side == 0 ? plan.d_w_absent : plan.d_w_present;
-    const int first = perm[0];
-    const int col_first = plan.d_colsum[first];
-    const int bin0 = side == 0 ? col_first : plan.n_genes - col_first;
-    const int add1 = w_other[first];
-
+    const uint32_t *hist = work.hist + p * work.hist_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    int carry = 0;
-    for (int base = 0; base < n; base += THREADS * ITEMS) {
-        const int k0 = base + tid * ITEMS;
-        int v[ITEMS];
+
+    for (int side = 0; side < 2; ++side) {
+        OutT *o = out + p * 2ll * n + static_cast<long long>(side) * n;
+        int carry = 0;
+        for (int base = 0; base < n; base += THREADS * ITEMS) {
+            const int k0 = base + tid * ITEMS;
+            int v[ITEMS];
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) v[i] = 0;
-        if (k0 < n) {
-            const int4 a = *reinterpret_cast<const int4 *>(h + k0);
-            const int4 b = *reinterpret_cast<const int4 *>(h + k0 + 4);
-            const uint4 pr = *reinterpret_cast<const uint4 *>(perm + k0);
-            v[0] = a.x + w_list[pr.x & 0xffffu];
-            v[1] = a.y + w_list[pr.x >> 16];
-            v[2] = a.z + w_list[pr.y & 0xffffu];
-            v[3] = a.w + w_list[pr.y >> 16];
-            v[4] = b.x + w_list[pr.z & 0xffffu];
-            v[5] = b.y + w_list[pr.z >> 16];
-            v[6] = b.z + w_list[pr.w & 0xffffu];
-            v[7] = b.w + w_list[pr.w >> 16];
-            if (k0 == 0) {
-                v[0] = bin0;
-                v[1] += add1;
+            for (int i = 0; i < ITEMS; ++i) v[i] = 0;
+            if constexpr (P16) {
+                const uint16_t *h = reinterpret_cast<const uint16_t *>(hist) + static_cast<long long>(side) * n;
+                if constexpr (VEC) {
+                    if (k0 < n) {
+                        const uint4 a = *reinterpret_cast<const uint4 *>(h + k0);
+                        v[0] = a.x & 0xffffu; v[1] = a.x >> 16; v[2] = a.y & 0xffffu; v[3] = a.y >> 16;
+                        v[4] = a.z & 0xffffu; v[5] = a.z >> 16; v[6] = a.w & 0xffffu; v[7] = a.w >> 16;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < ITEMS; ++i) if (k0 + i < n) v[i] = h[k0 + i];
+                }
+                // packed bins hold the steps of the curve: core[k] = core[0] - (losses up to k)
+                if (side == 1) {
+#pragma unroll
+                    for (int i = 0; i < ITEMS; ++i) if (k0 + i > 0) v[i] = -v[i];
+                }
+            } else {
+                const int32_t *h = reinterpret_cast<const int32_t *>(hist) + static_cast<long long>(side) * n;
+                if constexpr (VEC) {
+                    if (k0 < n) {
+                        const int4 a = *reinterpret_cast<const int4 *>(h + k0);
+                        const int4 b = *reinterpret_cast<const int4 *>(h + k0 + 4);
+                        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+                    }
+                } else {
+#pragma unroll
+                    for (int i = 0; i < ITEMS; ++i) if (k0 + i < n) v[i] = h[k0 + i];
+                }
             }
-        }
-        int run = 0;
+            int run = 0;
 #pragma unroll
-        for (int i = 0; i < ITEMS; ++i) {
-            run += v[i];
-            v[i] = run;
-        }
-        int incl = run;
+            for (int i = 0; i < ITEMS; ++i) {
+                run += v[i];
+                v[i] = run;
+            }
+            int incl = run;
 #pragma unroll
-        for (int off = 1; off < 32; off <<= 1) {
-            const int y = __shfl_up_sync(FULL_MASK, incl, off);
-            if (lane >= off) incl += y;
-        }
-        if (lane == 31) warp_tot[warp] = incl;
-        __syncthreads();
-        int before = 0, total = 0;
+            for (int off = 1; off < 32; off <<= 1) {
+                const int y = __shfl_up_sync(FULL_MASK, incl, off);
+                if (lane >= off) incl += y;
+            }
+            if (lane == 31) warp_tot[warp] = incl;
+            __syncthreads();                          // every load of this step has been issued and consumed
+            int before = 0, total = 0;
 #pragma unroll
-        for (int i = 0; i < THREADS / 32; ++i) {
-            const int wt = warp_tot[i];
-            if (i < warp) before += wt;
-            total += wt;
-        }
-        const int excl = carry + before + incl - run;
-        if (k0 < n) {
+            for (int i = 0; i < THREADS / 32; ++i) {
+                const int wt = warp_tot[i];
+                if (i < warp) before += wt;
+                total += wt;
+            }
+            const int excl = carry + before + incl - run;
 #pragma unroll
             for (int i = 0; i < ITEMS; ++i) {
                 const int c = excl + v[i];
-                v[i] = side == 0 ? c : plan.n_genes - c;
+                // int32 bins count the genes LOST so far on the core side; packed bins are already signed steps
+                v[i] = (!P16 && side == 1) ? plan.n_genes - c : c;
             }
-            if constexpr (sizeof(OutT) == 4) {
-                *reinterpret_cast<int4 *>(o + k0) = make_int4(v[0], v[1], v[2], v[3]);
-                *reinterpret_cast<int4 *>(o + k0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
+            if constexpr (VEC) {
+                if (k0 < n) {
+                    if constexpr (sizeof(OutT) == 4) {
+                        *reinterpret_cast<int4 *>(o + k0) = make_int4(v[0], v[1], v[2], v[3]);
+                        *reinterpret_cast<int4 *>(o + k0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < ITEMS; i += 2)
+                            *reinterpret_cast<double2 *>(o + k0 + i) = make_double2(static_cast<double>(v[i]), static_cast<double>(v[i + 1]));
+                    }
+                }
             } else {
 #pragma unroll
-                for (int i = 0; i < ITEMS; i += 2)
-                    *reinterpret_cast<double2 *>(o + k0 + i) = make_double2(static_cast<double>(v[i]), static_cast<double>(v[i + 1]));
+                for (int i = 0; i < ITEMS; ++i) if (k0 + i < n) o[k0 + i] = static_cast<OutT>(v[i]);
             }
+            carry += total;
+            __syncthreads();
         }
-        carry += total;
-        __syncthreads();
     }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Launch logic
+// ---------------------------------------------------------------------------------------------
 int check_plan(const pgx_plan *plan)
 {
     if (!plan) return fail(PGX_ERR_INVALID, "plan is null");
@@ -558,7 +686,14 @@ int check_plan(const pgx_plan *plan)
     if ((reinterpret_cast<uintptr_t>(plan->d_chunks) | reinterpret_cast<uintptr_t>(plan->d_tasks) |
          reinterpret_cast<uintptr_t>(plan->d_bits)) & 15)
         return fail(PGX_ERR_INVALID, "d_chunks, d_tasks and d_bits must be 16-byte aligned");
+    if (plan->max_colsum < 0) return fail(PGX_ERR_INVALID, "max_colsum < 0");
     return PGX_OK;
+}
+
+// uint16 histogram bins are exact whenever no genome holds more than 65,535 genes (0 = unknown: int32 bins)
+bool packed_bins(const pgx_plan *plan)
+{
+    return !g_wide_bins && plan->max_colsum > 0 && plan->max_colsum <= 65535;
 }
 
 struct DeviceLimits {
@@ -581,50 +716,90 @@ int device_limits(DeviceLimits *out)
     return PGX_OK;
 }
 
-template <int B>
-int launch_list(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm, int32_t *d_hist,
+// Register cap x threads of the list kernel: 1 = 48 x 1,024, 2 = 64 x 768 (the same share of the register file;
+// measured 2.5 % faster on C4).  PGX_LIST_VARIANT overrides the default.
+int list_variant()
+{
+    static const int v = [] {
+        const char *env = getenv("PGX_LIST_VARIANT");
+        const int x = env ? atoi(env) : 2;
+        return x == 1 ? 1 : 2;
+    }();
+    return v;
+}
+
+template <int B, bool P16>
+int launch_list(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm, const Work &work,
                 const DeviceLimits &lim, cudaStream_t stream)
 {
+    const int variant = list_variant();
     int threads = g_tuning.threads;
     if (threads <= 0 && getenv("PGX_LIST_THREADS")) threads = atoi(getenv("PGX_LIST_THREADS"));
     const size_t table_bytes = ((static_cast<size_t>(plan.n_genomes + SENTINELS) * B + 7) & ~size_t(7)) * sizeof(uint16_t);
-    if (threads <= 0) threads = table_bytes > 100 * 1024 ? 1024 : (table_bytes > 40 * 1024 ? 512 : 256);
+    if (threads <= 0) threads = table_bytes > 100 * 1024 ? (variant == 2 ? 768 : 1024) : (table_bytes > 40 * 1024 ? 512 : 256);
     threads = max(32, min(1024, (threads / 32) * 32));
     const size_t smem = table_bytes + static_cast<size_t>(threads / 32) * EVENT_QUEUE * sizeof(uint32_t);
-    PGX_CUDA(cudaFuncSetAttribute(list_kernel<B>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                  static_cast<int>(smem)));
+    auto kernel = variant == 2 ? list_kernel<B, 64, P16> : list_kernel<B, 48, P16>;
+    PGX_CUDA(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
     const long long batches = (n_perm + B - 1) / B;
-    // Row splits: enough CTAs for ~16 waves so the tail is small, but every CTA keeps at
+    // Row splits: enough CTAs for ~8 waves so the tail is small, but every CTA keeps at
     // least a few tasks per warp (the table build is amortised over them).
     int splits = g_tuning.row_splits;
     if (splits <= 0) {
         const long long resident = static_cast<long long>(lim.sm_count) *
                                    max(1, min(8, static_cast<int>((200 * 1024) / (smem + 1024))));
-        const long long want = (16 * resident + batches - 1) / batches;
+        const long long want = (8 * resident + batches - 1) / batches;
         const long long most = max(1ll, static_cast<long long>(plan.n_tasks) / ((threads / 32) * 2));
         splits = static_cast<int>(max(1ll, min(want, most)));
     }
     splits = max(1, min(splits, 65535));
     const long long n_items = batches * splits;
     int per_sm = 1;
-    PGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, list_kernel<B>, threads, smem));
+    PGX_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, threads, smem));
+    if (per_sm < 1) return fail(PGX_ERR_UNSUPPORTED, "list kernel does not fit an SM with %d threads", threads);
     const long long grid = max(1ll, min(n_items, static_cast<long long>(lim.sm_count) * max(1, per_sm)));
-    list_kernel<B><<<static_cast<unsigned>(grid), threads, smem, stream>>>(plan, d_perms, n_perm, d_hist, splits, n_items);
+    kernel<<<static_cast<unsigned>(grid), threads, smem, stream>>>(plan, d_perms, n_perm, work, splits, n_items);
     PGX_LAUNCH_CHECK("list_kernel");
     return PGX_OK;
 }
 
-int launch_probe(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm, int32_t *d_hist,
+template <bool P16>
+int launch_list_b(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm, const Work &work,
+                  const DeviceLimits &lim, cudaStream_t stream)
+{
+    const size_t per_perm = static_cast<size_t>(plan.n_genomes + SENTINELS) * sizeof(uint16_t);
+    const size_t budget = static_cast<size_t>(lim.smem_optin) - 64 - 32 * EVENT_QUEUE * sizeof(uint32_t);
+    int b = g_tuning.perms_per_cta;
+    if (b != 1 && b != 2 && b != 4 && b != 8) b = plan.perms_per_cta;
+    if (b != 1 && b != 2 && b != 4 && b != 8) b = 8;
+    while (b > 1 && per_perm * b > budget) b >>= 1;
+    if (per_perm * b > budget) return fail(PGX_ERR_UNSUPPORTED, "rank table does not fit shared memory");
+    switch (b) {
+        case 8: return launch_list<8, P16>(plan, d_perms, n_perm, work, lim, stream);
+        case 4: return launch_list<4, P16>(plan, d_perms, n_perm, work, lim, stream);
+        case 2: return launch_list<2, P16>(plan, d_perms, n_perm, work, lim, stream);
+        default: return launch_list<1, P16>(plan, d_perms, n_perm, work, lim, stream);
+    }
+}
+
+template <bool P16>
+int launch_probe(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm, const Work &work,
                  cudaStream_t stream)
 {
     // one warp per (superblock, permutation); 2^31 blocks of 4 warps cover any realistic call
     const long long units = n_perm * plan.n_superblocks;
     const long long blocks = (units + SLICE_WARPS - 1) / SLICE_WARPS;
     if (blocks > 2147483647ll) return fail(PGX_ERR_UNSUPPORTED, "too many (superblock, permutation) units in one call");
+    // PGX_PROBE_STRAGGLERS: pending genes from which a warp finishes its walk gene by gene (0 = never)
+    static const int straggler_max = [] {
+        const char *env = getenv("PGX_PROBE_STRAGGLERS");
+        return env ? max(0, atoi(env)) : 16;
+    }();
+    const unsigned grid = static_cast<unsigned>(blocks);
     switch (plan.slice_words) {
-        case 4: probe_kernel<4><<<static_cast<unsigned>(blocks), SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, d_hist); break;
-        case 2: probe_kernel<2><<<static_cast<unsigned>(blocks), SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, d_hist); break;
-        default: probe_kernel<1><<<static_cast<unsigned>(blocks), SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, d_hist); break;
+        case 4: probe_kernel<4, P16><<<grid, SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, work, straggler_max); break;
+        case 2: probe_kernel<2, P16><<<grid, SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, work, straggler_max); break;
+        default: probe_kernel<1, P16><<<grid, SLICE_WARPS * 32, 0, stream>>>(plan, d_perms, n_perm, work, straggler_max); break;
     }
     PGX_LAUNCH_CHECK("probe_kernel");
     return PGX_OK;
@@ -654,31 +829,30 @@ int aux_for_device(Aux **out)
     return PGX_OK;
 }
 
-template <typename OutT>
-int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, int32_t *d_hist,
-               OutT *d_out, cudaStream_t stream, Aux *own_aux = nullptr)
+// prep + the two row kernels of n_perm permutations into ``work`` (histogram rows complete when the stream is)
+template <bool P16>
+int run_rows(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, const Work &work, int *d_bad_rows,
+             cudaStream_t stream, Aux *own_aux, ProfileEvents *ev)
 {
-    if (int rc = check_plan(plan)) return rc;
-    if (n_perm < 0) return fail(PGX_ERR_INVALID, "n_perm < 0");
-    if (n_perm == 0) return PGX_OK;
-    if (!d_perms || !d_hist || !d_out) return fail(PGX_ERR_INVALID, "null permutation / output pointer");
     DeviceLimits lim;
     if (int rc = device_limits(&lim)) return rc;
     const int n = plan->n_genomes;
-    PGX_CUDA(cudaMemsetAsync(d_hist, 0, sizeof(int32_t) * 2ull * n * n_perm, stream));
-    ProfileEvents ev{};
-    const bool profile = g_profile_on;
-    if (profile) {
-        PGX_CUDA(cudaEventCreate(&ev.begin));
-        PGX_CUDA(cudaEventCreate(&ev.list_done));
-        PGX_CUDA(cudaEventCreate(&ev.probe_done));
-        PGX_CUDA(cudaEventCreate(&ev.end));
-        PGX_CUDA(cudaEventRecord(ev.begin, stream));
+    const size_t prep_smem = static_cast<size_t>(n) * sizeof(uint16_t);
+    if (prep_smem > 48 * 1024)
+        PGX_CUDA(cudaFuncSetAttribute(prep_kernel<P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prep_smem)));
+    for (long long p0 = 0; p0 < n_perm; p0 += 2147483647ll) {
+        const long long np = min(2147483647ll, n_perm - p0);
+        Work w = work;
+        w.hist += p0 * work.hist_stride;
+        w.ranks += p0 * work.rank_stride;
+        prep_kernel<P16><<<static_cast<unsigned>(np), 256, prep_smem, stream>>>(*plan, d_perms + p0 * n, w, d_bad_rows);
+        PGX_LAUNCH_CHECK("prep_kernel");
     }
+    if (ev) PGX_CUDA(cudaEventRecord(ev->prep_done, stream));
     // The two row kernels only add into the histogram, in any order: unless per-kernel timing is
     // on (or PGX_NO_OVERLAP is set), the probe kernel runs beside the list kernel on a second stream.
     Aux *aux = own_aux;
-    const bool overlap = !profile && !g_no_overlap && plan->n_tasks > 0 && plan->n_long > 0;
+    const bool overlap = !ev && !g_no_overlap && plan->n_tasks > 0 && plan->n_long > 0;
     if (overlap) {
         if (!aux) {
             if (int rc = aux_for_device(&aux)) return rc;
@@ -687,49 +861,313 @@ int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, 
         PGX_CUDA(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
     }
     if (plan->n_tasks > 0) {
-        const size_t per_perm = static_cast<size_t>(n + SENTINELS) * sizeof(uint16_t);
-        const size_t budget = static_cast<size_t>(lim.smem_optin) - 64 - 32 * EVENT_QUEUE * sizeof(uint32_t);
-        int b = g_tuning.perms_per_cta;
-        if (b != 1 && b != 2 && b != 4 && b != 8) b = plan->perms_per_cta;
-        if (b != 1 && b != 2 && b != 4 && b != 8) b = 8;
-        while (b > 1 && per_perm * b > budget) b >>= 1;
-        if (per_perm * b > budget) return fail(PGX_ERR_UNSUPPORTED, "rank table does not fit shared memory");
-        int rc;
-        switch (b) {
-            case 8: rc = launch_list<8>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
-            case 4: rc = launch_list<4>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
-            case 2: rc = launch_list<2>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
-            default: rc = launch_list<1>(*plan, d_perms, n_perm, d_hist, lim, stream); break;
-        }
-        if (rc) return rc;
+        if (int rc = launch_list_b<P16>(*plan, d_perms, n_perm, work, lim, stream)) return rc;
     }
-    if (profile) PGX_CUDA(cudaEventRecord(ev.list_done, stream));
+    if (ev) PGX_CUDA(cudaEventRecord(ev->list_done, stream));
     if (overlap) {
         // launched AFTER the list kernel: one list CTA per SM first, probe CTAs fill what is left
-        if (int rc = launch_probe(*plan, d_perms, n_perm, d_hist, aux->stream)) return rc;
+        if (int rc = launch_probe<P16>(*plan, d_perms, n_perm, work, aux->stream)) return rc;
         PGX_CUDA(cudaEventRecord(aux->join, aux->stream));
         PGX_CUDA(cudaStreamWaitEvent(stream, aux->join, 0));
     } else if (plan->n_long > 0) {
-        if (int rc = launch_probe(*plan, d_perms, n_perm, d_hist, stream)) return rc;
+        if (int rc = launch_probe<P16>(*plan, d_perms, n_perm, work, stream)) return rc;
     }
-    if (profile) PGX_CUDA(cudaEventRecord(ev.probe_done, stream));
+    if (ev) PGX_CUDA(cudaEventRecord(ev->probe_done, stream));
+    return PGX_OK;
+}
+
+template <typename OutT, bool P16>
+int launch_scan(const pgx_plan *plan, long long n_perm, const Work &work, OutT *d_out, cudaStream_t stream)
+{
+    const int n = plan->n_genomes;
     for (long long p0 = 0; p0 < n_perm; p0 += 2147483647ll) {
         const long long np = min(2147483647ll, n_perm - p0);
-        dim3 grid(static_cast<unsigned>(np), 2);
-        static const bool scan_v8 = getenv("PGX_SCAN_V8") != nullptr;       // experiment, see scan_kernel_v8
-        if (scan_v8 && n % 8 == 0)
-            scan_kernel_v8<OutT><<<grid, 256, 0, stream>>>(*plan, d_perms + p0 * n, d_hist + p0 * 2ll * n,
-                                                           d_out + p0 * 2ll * n);
-        else
-            scan_kernel<OutT><<<grid, 256, 0, stream>>>(*plan, d_perms + p0 * n, d_hist + p0 * 2ll * n,
-                                                        d_out + p0 * 2ll * n);
+        Work w = work;
+        w.hist += p0 * work.hist_stride;
+        const unsigned grid = static_cast<unsigned>(np);
+        // 16-byte accesses need 16-byte aligned rows: N % 8 == 0 and an aligned base
+        const bool vec = n % 8 == 0 && ((reinterpret_cast<uintptr_t>(w.hist) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0 &&
+                         (work.hist_stride % 4) == 0;
+        if (vec) scan_kernel<OutT, P16, true><<<grid, 256, 0, stream>>>(*plan, w, d_out + p0 * 2ll * n);
+        else scan_kernel<OutT, P16, false><<<grid, 256, 0, stream>>>(*plan, w, d_out + p0 * 2ll * n);
         PGX_LAUNCH_CHECK("scan_kernel");
     }
+    return PGX_OK;
+}
+
+// Curves of n_perm permutations: d_work is an int32 [n_perm][2N] buffer (the output itself for OutT = int32).
+template <typename OutT>
+int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, int32_t *d_work,
+               OutT *d_out, cudaStream_t stream, Aux *own_aux = nullptr)
+{
+    if (int rc = check_plan(plan)) return rc;
+    if (n_perm < 0) return fail(PGX_ERR_INVALID, "n_perm < 0");
+    if (n_perm == 0) return PGX_OK;
+    if (!d_perms || !d_work || !d_out) return fail(PGX_ERR_INVALID, "null permutation / output pointer");
+    const long long n = plan->n_genomes;
+    const bool p16 = packed_bins(plan);
+    ProfileEvents ev{};
+    const bool profile = g_profile_on;
+    if (profile) {
+        PGX_CUDA(cudaEventCreate(&ev.begin));
+        PGX_CUDA(cudaEventCreate(&ev.prep_done));
+        PGX_CUDA(cudaEventCreate(&ev.list_done));
+        PGX_CUDA(cudaEventCreate(&ev.probe_done));
+        PGX_CUDA(cudaEventCreate(&ev.end));
+        PGX_CUDA(cudaEventRecord(ev.begin, stream));
+    }
+    Work work;
+    uint16_t *scratch = nullptr;
+    if (p16) {
+        // row of 8N bytes: [rank row 2N | free 2N | packed histogram 4N]
+        work.hist = reinterpret_cast<uint32_t *>(d_work) + n;
+        work.hist_stride = 2 * n;
+        work.ranks = reinterpret_cast<uint16_t *>(d_work);
+        work.rank_stride = 4 * n;
+    } else {
+        // int32 bins fill the row: the rank rows go to stream-ordered scratch from the device's pool
+        PGX_CUDA(cudaMallocAsync(reinterpret_cast<void **>(&scratch), sizeof(uint16_t) * n * n_perm, stream));
+        work.hist = reinterpret_cast<uint32_t *>(d_work);
+        work.hist_stride = 2 * n;
+        work.ranks = scratch;
+        work.rank_stride = n;
+    }
+    int rc = p16 ? run_rows<true>(plan, d_perms, n_perm, work, nullptr, stream, own_aux, profile ? &ev : nullptr)
+                 : run_rows<false>(plan, d_perms, n_perm, work, nullptr, stream, own_aux, profile ? &ev : nullptr);
+    if (scratch) cudaFreeAsync(scratch, stream);
+    if (rc) return rc;
+    rc = p16 ? launch_scan<OutT, true>(plan, n_perm, work, d_out, stream)
+             : launch_scan<OutT, false>(plan, n_perm, work, d_out, stream);
+    if (rc) return rc;
     if (profile) {
         PGX_CUDA(cudaEventRecord(ev.end, stream));
         std::lock_guard<std::mutex> lock(g_profile_mu);
         g_profile_events.push_back(ev);
     }
+    return PGX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Host-buffer pipeline: permutations from host memory (or drawn from the numpy-legacy stream), curves into host
+// memory.  Blocks of permutations travel through three slots: while one block's rows go down to the host, the next
+// block's kernels run and the one after that uploads (or draws) its permutations.  With packed bins the device
+// ships the histogram rows themselves -- the curves' steps, uint16 -- into pinned staging and a few host threads
+// rebuild the curves straight into the caller's result; otherwise int32 / float64 curves are copied as they are.
+// ---------------------------------------------------------------------------------------------
+constexpr int SLOTS = 3;
+
+struct Slot {
+    cudaStream_t stream = nullptr;
+    cudaEvent_t done = nullptr;
+    Aux aux;
+    uint16_t *h_perm = nullptr;       // pinned; RNG mode only
+    uint16_t *d_perm = nullptr;
+    uint16_t *d_rank = nullptr;       // packed mode
+    uint32_t *d_hist = nullptr;       // packed mode: [block][N] words; wide mode: int32 [block][2N]
+    double *d_f64 = nullptr;          // wide mode, float64 output
+    uint16_t *h_rows = nullptr;       // pinned staging: packed rows (uint16 [block][2N]); wide mode: curves as they are
+};
+
+struct Pipe {
+    int device = -1;
+    long long block = 0, n = 0;
+    bool packed = false, f64 = false, rng = false;
+    int *bad_rows = nullptr;          // host-mapped counter of rows that are not permutations
+    Slot slot[SLOTS];
+};
+
+void release(Pipe &b)
+{
+    for (auto &s : b.slot) {
+        if (s.h_perm) cudaFreeHost(s.h_perm);
+        if (s.h_rows) cudaFreeHost(s.h_rows);
+        if (s.d_perm) cudaFree(s.d_perm);
+        if (s.d_rank) cudaFree(s.d_rank);
+        if (s.d_hist) cudaFree(s.d_hist);
+        if (s.d_f64) cudaFree(s.d_f64);
+        if (s.done) cudaEventDestroy(s.done);
+        if (s.stream) cudaStreamDestroy(s.stream);
+        if (s.aux.stream) cudaStreamDestroy(s.aux.stream);
+        if (s.aux.fork) cudaEventDestroy(s.aux.fork);
+        if (s.aux.join) cudaEventDestroy(s.aux.join);
+        s = Slot{};
+    }
+    if (b.bad_rows) cudaFreeHost(b.bad_rows);
+    b.bad_rows = nullptr;
+    b.device = -1;
+    b.block = b.n = 0;
+}
+
+int acquire(Pipe &b, int device, long long block, long long n, bool packed, bool f64, bool rng)
+{
+    if (b.device == device && b.n == n && b.block >= block && b.packed == packed && (b.f64 || !f64 || packed) &&
+        (b.rng || !rng))
+        return PGX_OK;
+    release(b);
+    PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&b.bad_rows), sizeof(int), cudaHostAllocMapped));
+    *b.bad_rows = 0;
+    for (auto &s : b.slot) {
+        PGX_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
+        PGX_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
+        PGX_CUDA(cudaStreamCreateWithFlags(&s.aux.stream, cudaStreamNonBlocking));
+        PGX_CUDA(cudaEventCreateWithFlags(&s.aux.fork, cudaEventDisableTiming));
+        PGX_CUDA(cudaEventCreateWithFlags(&s.aux.join, cudaEventDisableTiming));
+        s.aux.device = device;
+        if (rng) PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s.h_perm), sizeof(uint16_t) * block * n, cudaHostAllocDefault));
+        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_perm), sizeof(uint16_t) * block * n));
+        if (packed) {
+            PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_rank), sizeof(uint16_t) * block * n));
+            PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_hist), sizeof(uint32_t) * block * n));
+            PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s.h_rows), sizeof(uint16_t) * block * 2 * n, cudaHostAllocDefault));
+        } else {
+            PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_hist), sizeof(int32_t) * block * 2 * n));
+            if (f64) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_f64), sizeof(double) * block * 2 * n));
+            PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s.h_rows), (f64 ? sizeof(double) : sizeof(int32_t)) * block * 2 * n,
+                                   cudaHostAllocDefault));
+        }
+    }
+    b.device = device;
+    b.block = block;
+    b.n = n;
+    b.packed = packed;
+    b.f64 = f64;
+    b.rng = rng;
+    return PGX_OK;
+}
+
+std::mutex g_pipe_mu;              // one host-buffer call at a time per process (it owns the staging)
+Pipe g_pipe;
+
+// h_perms != nullptr: the caller's permutations; otherwise they are drawn from the numpy-legacy MT19937 state.
+int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_key, int32_t *mt_pos, long long n_perm,
+                  void *h_curves, bool out_f64, long long perms_per_block)
+{
+    const long long n = plan->n_genomes;
+    const bool rng = h_perms == nullptr;
+    const bool packed = packed_bins(plan);
+    long long block = perms_per_block;
+    if (block <= 0) {
+        // about 32 MB of packed rows per block: large enough for the list kernel's persistent CTAs to amortise their
+        // rank tables, small enough that the first upload and the last download, which nothing overlaps, stay short;
+        // the RNG-fed call is bound by the serial shuffle stream and takes smaller blocks so that its last one is short
+        block = rng ? std::max(32ll, std::min(4096ll, (8ll << 20) / (4 * n))) : std::max(64ll, std::min(1ll << 16, (32ll << 20) / (4 * n)));
+        block = (block + 7) / 8 * 8;
+    }
+    std::lock_guard<std::mutex> lock(g_pipe_mu);
+    int dev = 0;
+    PGX_CUDA(cudaGetDevice(&dev));
+    Pipe &buf = g_pipe;
+    // the staging is sized for the default block even when this call is shorter: the next call need not reallocate
+    if (int rc = acquire(buf, dev, perms_per_block > 0 ? std::min<long long>(block, std::max<long long>(n_perm, 8)) : block,
+                         n, packed, out_f64, rng))
+        return rc;
+    block = std::min<long long>(block, std::max<long long>(n_perm, 8));
+    const long long n_blocks = (n_perm + block - 1) / block;
+    *buf.bad_rows = 0;
+    int *d_bad_rows = nullptr;
+    PGX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_bad_rows), buf.bad_rows, 0));
+    {
+        // The result is usually fresh memory: ask for huge pages so that filling it costs one page
+        // fault per 2 MB instead of one per 4 KB (a hint; ignored where THP is off).
+        const size_t elem = out_f64 ? sizeof(double) : sizeof(int32_t);
+        const uintptr_t page = 2u << 20;
+        const uintptr_t lo = (reinterpret_cast<uintptr_t>(h_curves) + page - 1) & ~(page - 1);
+        const uintptr_t hi = (reinterpret_cast<uintptr_t>(h_curves) + elem * 2ull * n * n_perm) & ~(page - 1);
+        if (hi > lo) madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
+    }
+    // PGX_ESTIMATE_TRACE=1: per-block timeline of the pipeline on stderr (development aid)
+    const bool trace = getenv("PGX_ESTIMATE_TRACE") != nullptr;
+    const auto t0 = std::chrono::steady_clock::now();
+    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count(); };
+
+    // issuing thread (the caller): draws / uploads block k, enqueues its kernels and its download; the movers
+    // (copy threads) wait for block k's download and rebuild / copy its rows into the result.  Both sides poll atomic
+    // counters: on the virtualised hosts this runs on, waking a sleeping thread costs 0.2-0.5 ms.
+    std::atomic<long long> issued{0}, retired{0};
+    std::atomic<int> failed{0};
+    std::vector<std::atomic<int>> parts_done(static_cast<size_t>(n_blocks));
+    for (auto &c : parts_done) c.store(0, std::memory_order_relaxed);
+    int movers = std::max(1, std::min(rng ? 6 : 12, static_cast<int>(std::thread::hardware_concurrency()) - (rng ? 3 : 2)));
+    if (const char *env = getenv("PGX_COPY_THREADS")) movers = std::max(1, std::min(32, atoi(env)));
+    movers = static_cast<int>(std::max<long long>(1, std::min<long long>(movers, block * n / 32768)));
+    const size_t out_elem = out_f64 ? sizeof(double) : sizeof(int32_t);
+    auto mover = [&](int t) {
+        cudaSetDevice(dev);
+        for (long long k = 0; k < n_blocks; ++k) {
+            while (issued.load(std::memory_order_acquire) <= k) {
+                if (failed.load(std::memory_order_relaxed)) return;
+                std::this_thread::yield();
+            }
+            Slot &s = buf.slot[k % SLOTS];
+            if (cudaEventSynchronize(s.done) != cudaSuccess) {
+                failed.store(1);
+                return;
+            }
+            const long long p0 = k * block, cnt = std::min<long long>(block, n_perm - p0);
+            const long long r0 = cnt * t / movers, r1 = cnt * (t + 1) / movers;
+            char *dst = static_cast<char *>(h_curves) + out_elem * 2 * n * p0;
+            if (packed) {
+                expand_delta_rows(s.h_rows, r0, r1, n, dst, out_f64);
+            } else {
+                const size_t row = out_elem * 2 * n;
+                memcpy(dst + row * r0, reinterpret_cast<const char *>(s.h_rows) + row * r0, row * (r1 - r0));
+            }
+            if (parts_done[static_cast<size_t>(k)].fetch_add(1, std::memory_order_acq_rel) + 1 == movers) {
+                retired.store(k + 1, std::memory_order_release);     // blocks retire in order: every mover walks them in order
+                if (trace) fprintf(stderr, "[pgx trace] block %lld: in the result %.2f ms\n", k, since());
+            }
+        }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 0; t < movers; ++t) pool.emplace_back(mover, t);
+
+    int rc = PGX_OK;
+    for (long long k = 0; k < n_blocks && !rc; ++k) {
+        while (retired.load(std::memory_order_acquire) + SLOTS <= k) {
+            if (failed.load(std::memory_order_relaxed)) break;
+            std::this_thread::yield();
+        }
+        if (failed.load(std::memory_order_relaxed)) break;
+        Slot &s = buf.slot[k % SLOTS];
+        const long long p0 = k * block, cnt = std::min<long long>(block, n_perm - p0);
+        const double t_wait = since();
+        const uint16_t *src = h_perms ? h_perms + p0 * n : s.h_perm;
+        if (rng) rc = pgx_legacy_shuffles(mt_key, mt_pos, n, cnt, s.h_perm);
+        const double t_rng = since();
+        if (!rc && cudaMemcpyAsync(s.d_perm, src, sizeof(uint16_t) * cnt * n, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
+            rc = fail(PGX_ERR_CUDA, "H2D copy of the permutations failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (!rc && packed) {
+            Work work{s.d_hist, n, s.d_rank, n};
+            rc = run_rows<true>(plan, s.d_perm, cnt, work, d_bad_rows, s.stream, &s.aux, nullptr);
+            if (!rc && cudaMemcpyAsync(s.h_rows, s.d_hist, sizeof(uint16_t) * cnt * 2 * n, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
+                rc = fail(PGX_ERR_CUDA, "D2H copy of the curve steps failed: %s", cudaGetErrorString(cudaGetLastError()));
+        } else if (!rc) {
+            rc = out_f64 ? run_curves<double>(plan, s.d_perm, cnt, reinterpret_cast<int32_t *>(s.d_hist), s.d_f64, s.stream, &s.aux)
+                         : run_curves<int32_t>(plan, s.d_perm, cnt, reinterpret_cast<int32_t *>(s.d_hist),
+                                               reinterpret_cast<int32_t *>(s.d_hist), s.stream, &s.aux);
+            const void *from = out_f64 ? static_cast<const void *>(s.d_f64) : static_cast<const void *>(s.d_hist);
+            if (!rc && cudaMemcpyAsync(s.h_rows, from, out_elem * cnt * 2 * n, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
+                rc = fail(PGX_ERR_CUDA, "D2H copy of the curves failed: %s", cudaGetErrorString(cudaGetLastError()));
+        }
+        if (!rc && cudaEventRecord(s.done, s.stream) != cudaSuccess) rc = fail(PGX_ERR_CUDA, "event record failed");
+        if (trace) fprintf(stderr, "[pgx trace] block %lld: waited until %.2f, rng until %.2f, enqueued %.2f ms\n", k, t_wait, t_rng, since());
+        if (rc) {
+            failed.store(1);
+            break;
+        }
+        issued.store(k + 1, std::memory_order_release);
+    }
+    if (rc) failed.store(1);
+    for (auto &th : pool) th.join();
+    if (!rc && failed.load()) rc = fail(PGX_ERR_CUDA, "a block of curves failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
+    if (rc) {
+        char text[512];
+        snprintf(text, sizeof(text), "%s", pgx_last_error());
+        for (auto &s : buf.slot) cudaStreamSynchronize(s.stream);
+        return fail(rc, "%s", text);
+    }
+    if (packed && *buf.bad_rows)
+        return fail(PGX_ERR_INVALID, "%d of the %lld genome orders are not permutations of 0 .. %lld", *buf.bad_rows, n_perm, n - 1);
     return PGX_OK;
 }
 
@@ -760,156 +1198,8 @@ int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int6
     if (n_perm < 0) return pgx::fail(PGX_ERR_INVALID, "n_perm < 0");
     if (n_perm == 0) return PGX_OK;
     if (!h_perms || !h_curves) return pgx::fail(PGX_ERR_INVALID, "null host pointer");
-    const long long n = plan->n_genomes;
-    long long block = perms_per_block;
-    if (block <= 0) {
-        // ~64 MB of curves per block keeps both PCIe directions and the SMs busy at once.
-        block = (64ll << 20) / (2 * n * (out_f64 ? 8 : 4));
-        block = std::max(64ll, std::min(block, 1ll << 16));
-        block = (block + 7) / 8 * 8;
-    }
-    block = std::min<long long>(block, n_perm);
-    const size_t perm_bytes = sizeof(uint16_t) * n * block;
-    const size_t hist_bytes = sizeof(int32_t) * 2 * n * block;
-    const size_t out_bytes = out_f64 ? sizeof(double) * 2 * n * block : 0;
-
-    // Three slots: while one block's curves travel to the host, the next block's kernels run and the one
-    // after that uploads its permutations, so both PCIe directions and the SMs stay busy.
-    constexpr int SLOTS = 3;
-    cudaStream_t streams[SLOTS] = {nullptr, nullptr, nullptr};
-    uint16_t *d_perms[SLOTS] = {nullptr, nullptr, nullptr};
-    int32_t *d_hist[SLOTS] = {nullptr, nullptr, nullptr};
-    double *d_out[SLOTS] = {nullptr, nullptr, nullptr};
-    int rc = PGX_OK;
-    // Scratch comes from the device's default memory pool so that repeated calls reuse it.
-    {
-        int dev = 0;
-        cudaMemPool_t pool;
-        if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetDefaultMemPool(&pool, dev) == cudaSuccess) {
-            unsigned long long keep = ~0ull;
-            cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &keep);
-        }
-    }
-    auto cleanup = [&]() {
-        for (int s = 0; s < SLOTS; ++s) {
-            if (!streams[s]) continue;
-            if (d_perms[s]) cudaFreeAsync(d_perms[s], streams[s]);
-            if (d_hist[s]) cudaFreeAsync(d_hist[s], streams[s]);
-            if (d_out[s]) cudaFreeAsync(d_out[s], streams[s]);
-            cudaStreamSynchronize(streams[s]);
-            cudaStreamDestroy(streams[s]);
-        }
-    };
-#define PGX_TRY(expr)                                                                        \
-    do {                                                                                     \
-        cudaError_t e__ = (expr);                                                            \
-        if (e__ != cudaSuccess) {                                                            \
-            rc = pgx::fail(PGX_ERR_CUDA, "%s failed: %s", #expr, cudaGetErrorString(e__));   \
-            cleanup();                                                                       \
-            return rc;                                                                       \
-        }                                                                                    \
-    } while (0)
-    const int n_streams = static_cast<int>(std::min<long long>(SLOTS, (n_perm + block - 1) / block));
-    for (int s = 0; s < n_streams; ++s) {
-        PGX_TRY(cudaStreamCreateWithFlags(&streams[s], cudaStreamNonBlocking));
-        PGX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_perms[s]), perm_bytes, streams[s]));
-        PGX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_hist[s]), hist_bytes, streams[s]));
-        if (out_f64) PGX_TRY(cudaMallocAsync(reinterpret_cast<void **>(&d_out[s]), out_bytes, streams[s]));
-    }
-    int slot = 0;
-    for (long long p0 = 0; p0 < n_perm; p0 += block, slot = (slot + 1) % n_streams) {
-        const long long np = std::min<long long>(block, n_perm - p0);
-        cudaStream_t st = streams[slot];
-        PGX_TRY(cudaMemcpyAsync(d_perms[slot], h_perms + p0 * n, sizeof(uint16_t) * n * np,
-                                cudaMemcpyHostToDevice, st));
-        if (out_f64) {
-            rc = pgx::run_curves<double>(plan, d_perms[slot], np, d_hist[slot], d_out[slot], st);
-            if (rc) { cleanup(); return rc; }
-            PGX_TRY(cudaMemcpyAsync(static_cast<double *>(h_curves) + p0 * 2 * n, d_out[slot],
-                                    sizeof(double) * 2 * n * np, cudaMemcpyDeviceToHost, st));
-        } else {
-            rc = pgx::run_curves<int32_t>(plan, d_perms[slot], np, d_hist[slot], d_hist[slot], st);
-            if (rc) { cleanup(); return rc; }
-            PGX_TRY(cudaMemcpyAsync(static_cast<int32_t *>(h_curves) + p0 * 2 * n, d_hist[slot],
-                                    sizeof(int32_t) * 2 * n * np, cudaMemcpyDeviceToHost, st));
-        }
-    }
-    for (int s = 0; s < n_streams; ++s) PGX_TRY(cudaStreamSynchronize(streams[s]));
-#undef PGX_TRY
-    cleanup();
-    return PGX_OK;
+    return pgx::host_pipeline(plan, h_perms, nullptr, nullptr, n_perm, h_curves, out_f64 != 0, perms_per_block);
 }
-
-// estimate_pan_core_size in one call (pangenome_analysis.py:76-90): RNG stream, upload, kernels,
-// download.  Three slots of pinned staging + device buffers (cached per device for the life of the
-// library); a producer thread draws the shuffles of a block and enqueues its H2D copy, kernels and
-// D2H copy, the calling thread waits for finished blocks in order and moves them into the caller's
-// (ordinary, pageable) result.
-namespace pgx {
-namespace {
-
-struct EstimateSlot {
-    cudaStream_t stream = nullptr;
-    cudaEvent_t done = nullptr;
-    Aux aux;                          // second stream + fork/join events of this slot's kernels
-    uint16_t *h_perm = nullptr, *d_perm = nullptr;
-    int32_t *d_hist = nullptr;
-    double *d_out = nullptr, *h_out = nullptr;
-};
-
-struct EstimateBuffers {
-    int device = -1;
-    long long block = 0, n = 0;
-    EstimateSlot slot[3];
-};
-
-void release(EstimateBuffers &b)
-{
-    for (auto &s : b.slot) {
-        if (s.h_perm) cudaFreeHost(s.h_perm);
-        if (s.h_out) cudaFreeHost(s.h_out);
-        if (s.d_perm) cudaFree(s.d_perm);
-        if (s.d_hist) cudaFree(s.d_hist);
-        if (s.d_out) cudaFree(s.d_out);
-        if (s.done) cudaEventDestroy(s.done);
-        if (s.stream) cudaStreamDestroy(s.stream);
-        if (s.aux.stream) cudaStreamDestroy(s.aux.stream);
-        if (s.aux.fork) cudaEventDestroy(s.aux.fork);
-        if (s.aux.join) cudaEventDestroy(s.aux.join);
-        s = EstimateSlot{};
-    }
-    b.device = -1;
-    b.block = b.n = 0;
-}
-
-int acquire(EstimateBuffers &b, int device, long long block, long long n)
-{
-    if (b.device == device && b.n == n && b.block >= block) return PGX_OK;
-    release(b);
-    for (auto &s : b.slot) {
-        PGX_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
-        PGX_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        PGX_CUDA(cudaStreamCreateWithFlags(&s.aux.stream, cudaStreamNonBlocking));
-        PGX_CUDA(cudaEventCreateWithFlags(&s.aux.fork, cudaEventDisableTiming));
-        PGX_CUDA(cudaEventCreateWithFlags(&s.aux.join, cudaEventDisableTiming));
-        s.aux.device = device;
-        PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s.h_perm), sizeof(uint16_t) * block * n, cudaHostAllocDefault));
-        PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s.h_out), sizeof(double) * block * 2 * n, cudaHostAllocDefault));
-        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_perm), sizeof(uint16_t) * block * n));
-        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_hist), sizeof(int32_t) * block * 2 * n));
-        PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_out), sizeof(double) * block * 2 * n));
-    }
-    b.device = device;
-    b.block = block;
-    b.n = n;
-    return PGX_OK;
-}
-
-std::mutex g_estimate_mu;          // one estimate call at a time per process (it owns the staging)
-EstimateBuffers g_estimate_buffers;
-
-}  // namespace
-}  // namespace pgx
 
 int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_pos, int64_t n_iter,
                           double *h_curves, int64_t perms_per_block)
@@ -918,134 +1208,7 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
     if (n_iter < 0) return pgx::fail(PGX_ERR_INVALID, "n_iter < 0");
     if (!mt_key || !mt_pos || (!h_curves && n_iter > 0)) return pgx::fail(PGX_ERR_INVALID, "null pointer");
     if (n_iter == 0) return PGX_OK;
-    const long long n = plan->n_genomes;
-    long long block = perms_per_block;
-    if (block <= 0) block = std::max(32ll, std::min(4096ll, (32ll << 20) / (16 * n)));
-    std::lock_guard<std::mutex> lock(pgx::g_estimate_mu);
-    int dev = 0;
-    PGX_CUDA(cudaGetDevice(&dev));
-    pgx::EstimateBuffers &buf = pgx::g_estimate_buffers;
-    if (int rc = pgx::acquire(buf, dev, block, n)) return rc;
-    block = std::min<long long>(block, n_iter);
-    const long long n_blocks = (n_iter + block - 1) / block;
-    {
-        // The result is usually fresh memory: ask for huge pages so that filling it costs one page
-        // fault per 2 MB instead of one per 4 KB (a hint; ignored where THP is off).
-        const uintptr_t page = 2u << 20;
-        const uintptr_t lo = (reinterpret_cast<uintptr_t>(h_curves) + page - 1) & ~(page - 1);
-        const uintptr_t hi = (reinterpret_cast<uintptr_t>(h_curves) + sizeof(double) * 2ull * n * n_iter) & ~(page - 1);
-        if (hi > lo) madvise(reinterpret_cast<void *>(lo), hi - lo, MADV_HUGEPAGE);
-    }
-
-    // PGX_ESTIMATE_TRACE=1: per-block timeline of the pipeline on stderr (development aid)
-    const bool trace = getenv("PGX_ESTIMATE_TRACE") != nullptr;
-    const auto trace_t0 = std::chrono::steady_clock::now();
-    auto since = [&]() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - trace_t0).count(); };
-
-    // producer -> consumer hand-off: ``issued`` blocks have their GPU work enqueued, ``retired`` blocks
-    // have been copied out; slot of block k is k % 3, reusable once block k - 3 retired
-    std::mutex mu;
-    std::condition_variable cv;
-    long long issued = 0, retired = 0;
-    // EXPERIMENT, off unless PGX_ESTIMATE_SPIN=1 (never run on a GPU yet): the two sides poll atomic copies of the
-    // counters instead of sleeping on the condition variable -- a notify that finds a sleeper costs the notifier
-    // 0.2-0.5 ms on the virtualised hosts this runs on.
-    const bool spin = getenv("PGX_ESTIMATE_SPIN") != nullptr;
-    std::atomic<long long> a_issued{0}, a_retired{0};
-    auto publish = [&](bool wake) {                    // call with ``mu`` released
-        if (!spin || wake) cv.notify_all();
-    };
-    int producer_rc = PGX_OK;
-    char producer_err[512] = "";
-    std::thread producer([&]() {
-        cudaSetDevice(dev);
-        for (long long k = 0; k < n_blocks; ++k) {
-            if (spin) {
-                while (a_retired.load(std::memory_order_acquire) + 3 <= k) std::this_thread::yield();
-            } else {
-                std::unique_lock<std::mutex> lk(mu);
-                cv.wait(lk, [&] { return retired + 3 > k; });
-            }
-            pgx::EstimateSlot &s = buf.slot[k % 3];
-            const long long p0 = k * block, cnt = std::min<long long>(block, n_iter - p0);
-            const double t_wait = since();
-            int rc = pgx_legacy_shuffles(mt_key, mt_pos, n, cnt, s.h_perm);
-            const double t_rng = since();
-            if (!rc && cudaMemcpyAsync(s.d_perm, s.h_perm, sizeof(uint16_t) * cnt * n, cudaMemcpyHostToDevice, s.stream) != cudaSuccess)
-                rc = pgx::fail(PGX_ERR_CUDA, "H2D copy of the permutations failed");
-            if (!rc) rc = pgx::run_curves<double>(plan, s.d_perm, cnt, s.d_hist, s.d_out, s.stream, &s.aux);
-            if (!rc && cudaMemcpyAsync(s.h_out, s.d_out, sizeof(double) * cnt * 2 * n, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
-                rc = pgx::fail(PGX_ERR_CUDA, "D2H copy of the curves failed");
-            if (!rc && cudaEventRecord(s.done, s.stream) != cudaSuccess) rc = pgx::fail(PGX_ERR_CUDA, "event record failed");
-            if (trace) fprintf(stderr, "[pgx trace] block %lld: rng %.2f -> %.2f ms, enqueued %.2f ms\n", k, t_wait, t_rng, since());
-            {
-                std::lock_guard<std::mutex> lk(mu);
-                if (rc) {
-                    producer_rc = rc;
-                    snprintf(producer_err, sizeof(producer_err), "%s", pgx_last_error());   // thread-local text
-                }
-                issued = rc ? n_blocks : k + 1;
-                a_issued.store(issued, std::memory_order_release);
-            }
-            publish(false);
-            if (rc) return;
-        }
-    });
-    int rc = PGX_OK;
-    int copy_threads = std::max(1, std::min(6, static_cast<int>(std::thread::hardware_concurrency()) / 2));
-    if (const char *env = getenv("PGX_COPY_THREADS")) copy_threads = std::max(1, std::min(16, atoi(env)));
-    for (long long k = 0; k < n_blocks; ++k) {
-        if (spin) {
-            while (a_issued.load(std::memory_order_acquire) <= k) std::this_thread::yield();
-        }
-        {
-            std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return issued > k; });         // (already true when spinning)
-            if (producer_rc) break;
-        }
-        pgx::EstimateSlot &s = buf.slot[k % 3];
-        const long long p0 = k * block, cnt = std::min<long long>(block, n_iter - p0);
-        if (cudaEventSynchronize(s.done) != cudaSuccess) {
-            rc = pgx::fail(PGX_ERR_CUDA, "a block of curves failed on the device: %s", cudaGetErrorString(cudaGetLastError()));
-            std::lock_guard<std::mutex> lk(mu);
-            retired = n_blocks + 3;                     // let the producer run out
-            a_retired.store(retired, std::memory_order_release);
-            cv.notify_all();
-            break;
-        }
-        const double t_ready = since();
-        {
-            // staging -> result with a few threads: one core fills fresh pages at only ~5 GB/s (2,000 permutations of
-            // C4 on the box: 69 / 39 / 28 / 27 ms per call with 1 / 2 / 4 / 6 threads)
-            const size_t bytes = sizeof(double) * cnt * 2 * n;
-            char *dst = reinterpret_cast<char *>(h_curves + p0 * 2 * n);
-            const char *src = reinterpret_cast<const char *>(s.h_out);
-            const int parts = static_cast<int>(std::max<size_t>(1, std::min<size_t>(copy_threads, bytes >> 20)));   // >= 1 MB each
-            std::vector<std::thread> movers;
-            for (int t = 1; t < parts; ++t) {
-                const size_t lo = bytes / parts * t, hi = t + 1 == parts ? bytes : bytes / parts * (t + 1);
-                movers.emplace_back([=]() { memcpy(dst + lo, src + lo, hi - lo); });
-            }
-            memcpy(dst, src, parts > 1 ? bytes / parts : bytes);
-            for (auto &m : movers) m.join();
-        }
-        {
-            std::lock_guard<std::mutex> lk(mu);
-            retired = k + 1;
-            a_retired.store(retired, std::memory_order_release);
-        }
-        publish(false);
-        if (trace) fprintf(stderr, "[pgx trace] block %lld: on the host %.2f ms, copied out %.2f ms\n", k, t_ready, since());
-    }
-    {
-        std::lock_guard<std::mutex> lk(mu);
-        retired = n_blocks + 3;
-        a_retired.store(retired, std::memory_order_release);
-    }
-    cv.notify_all();
-    producer.join();
-    if (producer_rc) return pgx::fail(producer_rc, "%s", producer_err);
-    return rc;
+    return pgx::host_pipeline(plan, nullptr, mt_key, mt_pos, n_iter, h_curves, true, perms_per_block);
 }
 
 int pgx_profile_enable(int32_t on)
@@ -1059,15 +1222,17 @@ int pgx_profile_read(double *list_ms, double *probe_ms, double *scan_ms, int64_t
     std::lock_guard<std::mutex> lock(pgx::g_profile_mu);
     double a = 0.0, b = 0.0, c = 0.0;
     for (auto &ev : pgx::g_profile_events) {
-        float t0 = 0.f, t1 = 0.f, t2 = 0.f;
+        float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
         PGX_CUDA(cudaEventSynchronize(ev.end));
-        PGX_CUDA(cudaEventElapsedTime(&t0, ev.begin, ev.list_done));
-        PGX_CUDA(cudaEventElapsedTime(&t1, ev.list_done, ev.probe_done));
-        PGX_CUDA(cudaEventElapsedTime(&t2, ev.probe_done, ev.end));
-        a += t0;
-        b += t1;
-        c += t2;
+        PGX_CUDA(cudaEventElapsedTime(&t0, ev.begin, ev.prep_done));
+        PGX_CUDA(cudaEventElapsedTime(&t1, ev.prep_done, ev.list_done));
+        PGX_CUDA(cudaEventElapsedTime(&t2, ev.list_done, ev.probe_done));
+        PGX_CUDA(cudaEventElapsedTime(&t3, ev.probe_done, ev.end));
+        a += t1;
+        b += t2;
+        c += t0 + t3;                    // prep + scan: everything that is not a row kernel
         cudaEventDestroy(ev.begin);
+        cudaEventDestroy(ev.prep_done);
         cudaEventDestroy(ev.list_done);
         cudaEventDestroy(ev.probe_done);
         cudaEventDestroy(ev.end);

@@ -115,7 +115,8 @@ class PanCoreEngine:
             d_colsum=ptr["colsum"], d_w_present=ptr["w_present"], d_w_absent=ptr["w_absent"],
             n_chunks=hp.n_chunks, n_genomes=hp.n_genomes, n_genes=hp.n_genes,
             n_rows=hp.n_rows, n_tasks=hp.n_tasks, n_long=hp.n_long,
-            n_superblocks=hp.n_superblocks, perms_per_cta=hp.perms_per_cta, slice_words=hp.slice_words)
+            n_superblocks=hp.n_superblocks, perms_per_cta=hp.perms_per_cta, slice_words=hp.slice_words,
+            max_colsum=int(hp.colsum.max()) if hp.colsum.size else 0, reserved_i32=0)
 
     # ---- device-resident path -------------------------------------------------------
     def curves_device(self, perms, out=None):

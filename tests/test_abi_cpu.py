@@ -20,12 +20,13 @@ def test_library_exports_every_declared_symbol():
     lib = _native.load()
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.pgx_version() == 200
+    assert lib.pgx_version() == 300
 
 
 def test_plan_struct_layout_matches_header():
-    # 9 pointers + int64 + 8 int32 = 112 bytes, no padding surprises
-    assert ctypes.sizeof(_native.PgxPlan) == 9 * 8 + 8 + 8 * 4
+    # 9 pointers + int64 + 10 int32 = 120 bytes, no padding surprises
+    assert ctypes.sizeof(_native.PgxPlan) == 9 * 8 + 8 + 10 * 4
+    assert _native.PgxPlan.max_colsum.offset == 9 * 8 + 8 + 8 * 4
 
 
 def test_invalid_arguments_set_last_error():
@@ -188,3 +189,26 @@ def test_legacy_shuffles_worker_pool_reuse_sleep_and_fork(monkeypatch):
         os._exit(0 if np.array_equal(engine.draw_legacy_permutations(1000, 300), want) else 1)
     _, status = os.waitpid(pid, 0)
     assert os.WIFEXITED(status) and os.WEXITSTATUS(status) == 0
+
+
+@pytest.mark.parametrize("n,rows,f64", [(1, 5, 0), (2, 3, 1), (7, 4, 0), (8, 9, 1), (9, 2, 0), (400, 33, 1), (10000, 17, 0), (10000, 5, 1)])
+def test_expand_deltas_rebuilds_the_curves(n, rows, f64):
+    """pgx_expand_deltas (the host half of the compact transfer) against numpy: steps -> curves."""
+    rng = np.random.RandomState(n + rows)
+    pan = np.cumsum(rng.randint(0, 4000, size=(rows, n)), axis=1).astype(np.int64)
+    core = pan[:, :1] - np.concatenate((np.zeros((rows, 1), dtype=np.int64),
+                                        np.cumsum(rng.randint(0, 3, size=(rows, max(n - 1, 0))), axis=1)), axis=1)
+    steps = np.empty((rows, 2 * n), dtype=np.uint16)
+    steps[:, :n] = np.diff(pan, axis=1, prepend=0)
+    steps[:, n] = core[:, 0]
+    steps[:, n + 1:] = -np.diff(core, axis=1)
+    out = np.full((rows, 2 * n), -1, dtype=np.float64 if f64 else np.int32)
+    for threads in (1, 3):
+        out[:] = -1
+        _native.check(_native.load().pgx_expand_deltas(steps.ctypes.data, rows, n, out.ctypes.data, f64, threads))
+        assert np.array_equal(out, np.hstack([pan, core]).astype(out.dtype))
+    # the largest step a table can have
+    big = np.zeros((1, 2 * n), dtype=np.uint16)
+    big[0, 0] = big[0, n] = 65535
+    _native.check(_native.load().pgx_expand_deltas(big.ctypes.data, 1, n, out.ctypes.data, f64, 1))
+    assert out[0, 0] == 65535 and out[0, n - 1] == 65535 and out[0, 2 * n - 1] == 65535

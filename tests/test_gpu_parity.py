@@ -7,7 +7,7 @@ import pytest
 import scipy.sparse
 
 import oracle
-from conftest import CURVE_CASES, draw_perms, golden_matrix, load_golden
+from conftest import BIG_CURVE_CASES, CURVE_CASES, config_matrix_cached, draw_perms, golden_matrix, load_golden
 
 pytestmark = pytest.mark.gpu
 
@@ -17,7 +17,8 @@ LL_RTOL = 1e-9
 @pytest.fixture(scope="module")
 def engine_mod():
     import torch
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device (run with -m gpu on the B200 box)")
     from pangenomix_b200 import _native, engine
     _native.load()
     yield engine
@@ -44,6 +45,25 @@ def test_curves_match_reference_fixtures(engine_mod, name):
     d_perms = torch.from_numpy(perms.view(np.int16)).cuda()
     got_dev = eng.curves_device(d_perms).cpu().numpy()
     assert np.array_equal(got_dev, want)
+
+
+@pytest.mark.parametrize("name", BIG_CURVE_CASES)
+def test_curves_match_live_reference_at_full_size(engine_mod, name):
+    """Configs C2 and C4 at BASELINE.json's full size against curves the LIVE reference computed for the same table
+    and seed (tests/golden/make_golden.py --big): 64 permutations of C2, 4 of C4; both C-ABI paths."""
+    import torch
+    g = load_golden(name)
+    coo = golden_matrix(name, g)
+    eng = engine_mod.PanCoreEngine(coo)
+    num_iter = int(g["num_iter"])
+    np.random.seed(int(g["seed"]))
+    perms = engine_mod.draw_legacy_permutations(coo.shape[1], num_iter)
+    want = g["curves"]
+    assert np.array_equal(eng.curves_host(perms), want)
+    assert np.array_equal(eng.curves_host(perms, out_f64=True), want.astype(np.float64))
+    assert np.array_equal(eng.curves_device(torch.from_numpy(perms.view(np.int16)).cuda()).cpu().numpy(), want)
+    np.random.seed(int(g["seed"]))
+    assert np.array_equal(eng.estimate(num_iter), want.astype(np.float64))
 
 
 @pytest.mark.parametrize("name", ["kat_6x5", "synth_800x50_s0", "c1_8000x50", "c2slice_4000x400"])
@@ -237,8 +257,9 @@ def test_degenerate_shapes(engine_mod):
 def test_c2_full_size_properties_and_spot_parity(engine_mod):
     """Config C2 (40,000 x 400, 1,000 permutations): size-independent invariants on every
     curve, oracle parity on a sample of them."""
-    from pangenomix_b200 import synth
-    coo = synth.config_matrix("c2")
+    import os
+    from oracle import cport
+    coo = config_matrix_cached("c2")
     eng = engine_mod.PanCoreEngine(coo)
     n, g = 400, 40000
     np.random.seed(12345)
@@ -251,8 +272,10 @@ def test_c2_full_size_properties_and_spot_parity(engine_mod):
     assert np.all(pan[:, -1] == np.count_nonzero(counts)) and np.all(core[:, -1] == np.count_nonzero(counts == n))
     col_sums = np.asarray(coo.sum(axis=0)).ravel()
     assert np.array_equal(pan[:, 0], col_sums[perms[:, 0]])
-    sample = [0, 1, 499, 999]
-    assert np.array_equal(curves[sample], _oracle_curves(coo, perms[sample]))
+    sample = np.r_[0:8, 496:504, 952:1000]                                  # 64 curves against the oracle's C port
+    ref_pan, ref_core = cport.curves_direct(coo, perms[sample].astype(np.int32), n_threads=os.cpu_count() or 1)
+    assert np.array_equal(curves[sample], np.hstack([ref_pan, ref_core]).astype(np.int32))
+    assert np.array_equal(curves[[0, 999]], _oracle_curves(coo, perms[[0, 999]]))
     # determinism and independence from the batch a permutation lands in
     again = eng.curves_host(perms[::-1].copy())[::-1]
     assert np.array_equal(again, curves)
@@ -279,8 +302,8 @@ def test_c4_full_size_properties_and_spot_parity(engine_mod):
     back-to-back kernel schedules must agree bit for bit."""
     import os
     from oracle import build as oracle_build, cport
-    from pangenomix_b200 import _native, synth
-    coo = synth.config_matrix("c4")
+    from pangenomix_b200 import _native
+    coo = config_matrix_cached("c4")
     eng = engine_mod.PanCoreEngine(coo)
     hp = eng.host_plan
     assert hp.n_long > 0 and hp.n_rows > 0 and hp.perms_per_cta == 8
@@ -297,7 +320,7 @@ def test_c4_full_size_properties_and_spot_parity(engine_mod):
     assert np.array_equal(pan[:, 0], col_sums[perms[:, 0]])
     # sum over k of pan[k] = sum over genes of (N - first presence): a checksum of checksums against numpy
     oracle_build.build()
-    sample = [0, 999]
+    sample = np.r_[0:24, 488:512, 984:1000]                                 # 64 curves against the oracle's C port
     ref_pan, ref_core = cport.curves_direct(coo, perms[sample].astype(np.int32), n_threads=os.cpu_count() or 1)
     assert np.array_equal(curves[sample], np.hstack([ref_pan, ref_core]).astype(np.int32))
     # per-kernel timing mode runs the row kernels back to back instead of side by side
@@ -308,6 +331,75 @@ def test_c4_full_size_properties_and_spot_parity(engine_mod):
         _native.profile_enable(False)
         _native.profile_read()
     assert np.array_equal(again, curves[:200])
+
+
+def test_c5_full_size_spot_parity(engine_mod):
+    """Config C5 at BASELINE.json's full size (2,000,000 alleles x 50,000 genomes, nnz 2.0e8): 2 permutations per
+    list CTA, 32-lane wavefront groups, ~150,000 bitmap rows.  16 curves bit for bit against the oracle's C port of
+    pangenome_analysis.py:81-90 (run in full: 16 x 1e11 cell visits on all host threads), invariants on 64."""
+    import os
+    from oracle import build as oracle_build, cport
+    coo = config_matrix_cached("c5")
+    n, g = 50000, 2000000
+    assert coo.shape == (g, n) and coo.nnz > 150_000_000
+    eng = engine_mod.PanCoreEngine(coo)
+    hp = eng.host_plan
+    assert hp.perms_per_cta == 2 and hp.n_long > 100000 and hp.n_rows > 500000
+    np.random.seed(12345)
+    perms = engine_mod.draw_legacy_permutations(n, 64)
+    curves = eng.curves_host(perms)
+    pan, core = curves[:, :n], curves[:, n:]
+    counts = np.bincount(coo.row, minlength=g)
+    assert np.all(np.diff(pan, axis=1) >= 0) and np.all(np.diff(core, axis=1) <= 0)
+    assert np.array_equal(pan[:, 0], core[:, 0])
+    assert np.all(pan[:, -1] == np.count_nonzero(counts)) and np.all(core[:, -1] == np.count_nonzero(counts == n))
+    col_sums = np.bincount(coo.col, minlength=n)
+    assert np.array_equal(pan[:, 0], col_sums[perms[:, 0]])
+    oracle_build.build()
+    threads = os.cpu_count() or 1
+    sample = np.r_[0:8, 56:64]
+    gm = cport.GenomeMajor(coo)
+    del coo
+    ref_pan, ref_core = cport.curves_direct(gm, perms[sample].astype(np.int32), n_threads=min(threads, 16))
+    assert np.array_equal(curves[sample], np.hstack([ref_pan, ref_core]).astype(np.int32))
+    # the reference-facing call on the same table: float64, the same rows
+    np.random.seed(12345)
+    assert np.array_equal(eng.estimate(8), curves[:8].astype(np.float64))
+
+
+def test_genomes_above_65535_genes_use_int32_bins(engine_mod):
+    """A table whose genomes hold more than 65,535 genes cannot count in uint16 bins: the int32 path of every
+    kernel, natively (not through PGX_WIDE_BINS)."""
+    import torch
+    rng = np.random.RandomState(7)
+    dens = np.concatenate([np.full(68000, 0.985), rng.uniform(0.0, 1.0, size=4000)])
+    x = (rng.random_sample((dens.size, 48)) < dens[:, None]).astype(np.int64)
+    coo = scipy.sparse.coo_matrix(x)
+    eng = engine_mod.PanCoreEngine(coo, long_threshold=12)
+    assert eng.c_plan.max_colsum > 65535 and eng.host_plan.n_long > 0 and eng.host_plan.n_rows > 0
+    perms = draw_perms(3, 48, 21).astype(np.uint16)
+    want = _oracle_curves(coo, perms)
+    assert want.max() > 65535
+    assert np.array_equal(eng.curves_host(perms), want)
+    assert np.array_equal(eng.curves_host(perms, out_f64=True, perms_per_block=8), want.astype(np.float64))
+    assert np.array_equal(eng.curves_device(torch.from_numpy(perms.view(np.int16)).cuda()).cpu().numpy(), want)
+    np.random.seed(3)
+    assert np.array_equal(eng.estimate(21), want.astype(np.float64))
+
+
+def test_rows_that_are_not_permutations_are_reported(engine_mod):
+    from pangenomix_b200 import _native
+    coo = _mixed_matrix(300)
+    eng = engine_mod.PanCoreEngine(coo, long_threshold=20)
+    perms = draw_perms(3, 300, 12).astype(np.uint16)
+    bad = perms.copy()
+    bad[5, 17] = bad[5, 18]                                  # one genome twice, another never
+    with pytest.raises(_native.PgxError, match="not permutations"):
+        eng.curves_host(bad)
+    bad[5, 17] = 40000                                       # out of range
+    with pytest.raises(_native.PgxError, match="not permutations"):
+        eng.curves_host(bad)
+    assert np.array_equal(eng.curves_host(perms), _oracle_curves(coo, perms))     # the engine is still usable
 
 
 def test_estimate_blocks_progress_and_rng_state(engine_mod, capsys):
