@@ -67,6 +67,9 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="weak (default, what the driver runs): every GPU rarefies the config's permutation count; "
+                         "strong: the config's permutations are split over the GPUs, as BASELINE.json words C4")
     return ap.parse_args()
 
 
@@ -93,13 +96,15 @@ def load_matrix(name, rank, barrier):
     return scipy.sparse.coo_matrix((data, (packed[0], packed[1])), shape=(n_genes, n_genomes))
 
 
-def workload_config(name, coo, perms, world):
+def workload_config(name, coo, perms, world, scaling="weak"):
     return {
         "workload": "%s: estimate_pan_core_size on a synthetic %d-genome x %d-gene presence/absence "
-                    "table (nnz %d), %d permutations per GPU per step" % (
-                        name.upper(), coo.shape[1], coo.shape[0], coo.nnz, perms),
+                    "table (nnz %d), %d permutations %s per step" % (
+                        name.upper(), coo.shape[1], coo.shape[0], coo.nnz, perms,
+                        "per GPU" if scaling == "weak" else "split over the GPUs"),
         "n_genomes": int(coo.shape[1]), "n_genes": int(coo.shape[0]), "nnz": int(coo.nnz),
-        "perms_per_gpu": int(perms), "parallelism": "permutation shards x%d, table replicated" % world,
+        "perms_per_gpu": int(perms if scaling == "weak" else -(-perms // world)),
+        "parallelism": "permutation shards x%d, table replicated" % world,
     }
 
 
@@ -255,7 +260,15 @@ def run_b200(args, rank, world, local_rank):
     l2_bytes = int(_native.device_info()["l2_bytes"])
     coo = load_matrix(args.workload, rank, barrier)
     n_genes, n = coo.shape
-    perms_n = args.perms or synth.CONFIGS[args.workload][4]
+    perms_total = args.perms or synth.CONFIGS[args.workload][4]
+    if args.scaling == "strong":
+        from pangenomix_b200.distributed import shard_bounds
+        lo, hi = shard_bounds(perms_total, world, rank)            # contiguous blocks, as the multi-GPU API shards
+        perms_n = hi - lo
+        perms_all = perms_total
+    else:
+        perms_n = perms_total
+        perms_all = perms_total * world
     t = time.time()
     eng = engine.PanCoreEngine(coo, device=device)
     hp = eng.host_plan
@@ -277,8 +290,11 @@ def run_b200(args, rank, world, local_rank):
     d_out = d_outs[0]
     gather = None
     if world > 1:
-        from pangenomix_b200.distributed import CurveGather
-        gather = CurveGather(perms_n, 2 * n, device, dst=0, n_buffers=n_buf,
+        from pangenomix_b200.distributed import CurveGather, shard_bounds as _sb
+        rows_max = _sb(perms_total, world, 0)[1] if args.scaling == "strong" else perms_n
+        if rows_max != perms_n:                  # ragged strong-scaling shards: the gather moves equal blocks
+            d_outs = [torch.zeros((rows_max, 2 * n), dtype=torch.int32, device=device) for _ in range(n_buf)]
+        gather = CurveGather(rows_max, 2 * n, device, dst=0, n_buffers=n_buf,
                              prefer_peer=os.environ.get("PGX_GATHER", "peer") != "nccl")
         log("[bench r%d] curve gather: %s%s" % (rank, gather.mode,
                                                  "" if gather.mode == "peer-push" else " (%s)" % getattr(gather, "fallback_reason", "requested")))
@@ -289,7 +305,7 @@ def run_b200(args, rank, world, local_rank):
         step_no[0] += 1
         if gather is not None:
             gather.before_overwrite(b)        # the buffer's previous transfer has read it
-        eng.curves_device(d_perms, out=d_outs[b])
+        eng.curves_device(d_perms, out=d_outs[b][:perms_n])
         if gather is not None:
             gather.send(b, d_outs[b])
 
@@ -349,6 +365,7 @@ def run_b200(args, rank, world, local_rank):
     # (the library then runs the two row kernels back to back instead of side by side)
     _native.profile_read()
     _native.profile_enable(True)
+    d_out = d_outs[0][:perms_n]
     for _ in range(min(args.steps, 3)):
         eng.curves_device(d_perms, out=d_out)
     torch.cuda.synchronize()
@@ -364,9 +381,9 @@ def run_b200(args, rank, world, local_rank):
             b_last = (step_no[0] - 1) % n_buf
             got = gather.gathered(b_last)
             assert torch.equal(got[0], d_outs[b_last])
-            far = got[world - 1][:16].cpu().numpy()
+            far = got[world - 1][:min(16, perms_n)].cpu().numpy()
             assert np.all(np.diff(far[:, :n], axis=1) >= 0) and np.array_equal(far[:, 0], far[:, n])
-            assert far[:, n - 1].min() > 0 and not np.array_equal(far, d_outs[b_last][:16].cpu().numpy())
+            assert far[:, n - 1].min() > 0 and not np.array_equal(far, d_outs[b_last][:min(16, perms_n)].cpu().numpy())
         barrier()
 
     # parity guard on the timed output (size-independent invariants, cheap)
@@ -392,10 +409,14 @@ def run_b200(args, rank, world, local_rank):
         if world > 1:
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         assert np.array_equal(h_out[:64], curves)
-        e2e = {"value": world * perms_n * args.steps / float(dt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": int(h_perms.nbytes) * world, "d2h_bytes_per_step": int(h_out.nbytes) * world,
+        packed = 0 < eng.c_plan.max_colsum <= 65535 and not os.environ.get("PGX_WIDE_BINS")
+        e2e = {"value": perms_all * args.steps / float(dt.item()), "unit": UNIT,
+               "h2d_bytes_per_step": 2 * n * perms_all, "d2h_bytes_per_step": (4 if packed else 8) * n * perms_all,
                "ms_per_step": float(dt.item()) / args.steps * 1e3,
-               "path": "pgx_pan_core_curves_host: pinned uint16 permutations in, int32 curves out, wall clock",
+               "path": "pgx_pan_core_curves_host: pinned uint16 permutations in, int32 curves out in host memory, wall clock; "
+                       + ("the device ships the curves' uint16 steps (4N bytes per permutation), host threads rebuild the "
+                          "int32 curves in the caller's buffer inside the timed region" if packed else
+                          "int32 curves cross PCIe as they are (a genome holds more than 65,535 genes)"),
                "host_rng_s_per_step_not_included": host_rng_s}
         del h_out, h_out_owner
     if sampler:
@@ -465,7 +486,7 @@ def run_b200(args, rank, world, local_rank):
             dist.destroy_process_group()
         return
 
-    value = world * perms_n * args.steps / (ms_total / 1e3)
+    value = perms_all * args.steps / (ms_total / 1e3)
     peak, peak_src = measured_peak()
     a_perm = hp.algorithmic_bytes_per_perm
     calls = max(1, calls)
@@ -511,7 +532,7 @@ def run_b200(args, rank, world, local_rank):
                "sample": "%d permutations of the same table (of %d), oracle C port of "
                          "pangenome_analysis.py:81-90, %d threads" % (sample_perms.shape[0], perms_n, threads),
                "single_thread_s_per_perm": t1}
-    config = workload_config(args.workload, coo, perms_n, world)
+    config = workload_config(args.workload, coo, perms_total, world, args.scaling)
     if flush is None:
         config["l2_policy"] = "inputs larger than L2: %.0f MB of permutations + %.0f MB of curves + %.0f MB of folded rows per step" % (
             d_perms.numel() * 2 / 1e6, d_out.numel() * 4 / 1e6, hp.streamed_bytes_per_pass / 1e6)
@@ -532,7 +553,7 @@ def run_b200(args, rank, world, local_rank):
     line = {
         "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
         "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": config,
+        "scaling": args.scaling, "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": config,
         "cells_per_s": value * n_genes * n, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks, "host_rng_s_for_perms": host_rng_s, "api": api, "heaps": heaps,
     }

@@ -41,8 +41,9 @@ enum {
 };
 
 /* Device-resident plan of a BINARY gene x genome presence/absence table, built once per
- * matrix by the host (pangenomix_b200/plan.py) from ``df_genes.data`` -- the same object
- * estimate_pan_core_size reads at pangenome_analysis.py:74.  Genes fall into three groups:
+ * matrix by pgx_plan_create (below; pangenomix_b200/plan.py is its numpy specification) from
+ * ``df_genes.data`` -- the same object estimate_pan_core_size reads at pangenome_analysis.py:74.
+ * Genes fall into three groups:
  *
  *  closed forms  Empty, universal, single-genome and single-absence genes never reach a row
  *                kernel: they are functions of perm[0] and of one rank and live in the
@@ -88,6 +89,48 @@ typedef struct pgx_plan {
                                       the host-buffer calls ship uint16 curve steps (0 = unknown: int32 everywhere) */
     int32_t reserved_i32;
 } pgx_plan;
+
+/* Host image of a plan: what pgx_host_plan_create makes of the COO table and pgx_plan_upload copies to the device.
+ * All arrays are owned by the image (pgx_host_plan_destroy frees them); sizes as in struct pgx_plan.  The row_* /
+ * long_gene arrays say which gene became which list / bitmap row (diagnostics and tests). */
+typedef struct pgx_host_plan {
+    void *owner;
+    const uint16_t *chunks;        /* [n_chunks * 8] */
+    const int32_t *tasks;          /* [n_tasks * 4] */
+    const uint16_t *sorted_idx;    /* [n_sorted] */
+    const int32_t *sorted_ptr;     /* [n_rows + 1] */
+    const uint32_t *bits;          /* [n_bits_words] */
+    const int32_t *colsum, *w_present, *w_absent;   /* [n_genomes] each */
+    const int64_t *row_gene;       /* [n_rows] gene of every list row */
+    const int32_t *row_len;        /* [n_rows] folded list length */
+    const uint8_t *row_absent;     /* [n_rows] 1 when the list holds the ABSENT genomes */
+    const int64_t *long_gene;      /* [n_long] gene of every bitmap row */
+    int64_t nnz, nnz_list, nnz_long, n_chunks, n_bits_words, n_sorted;
+    int32_t n_genomes, n_genes, n_rows, n_tasks, n_long, n_superblocks, perms_per_cta, slice_words;
+    int32_t long_threshold, max_colsum, n_empty, n_full;
+} pgx_host_plan;
+
+/* The planner (host only, threaded; no GPU work): COO entries of a BINARY gene x genome table -- row = gene,
+ * col = genome, every entry a presence, as every producer of the reference writes ``df_genes.data``
+ * (pangenome.py:631-650; read back by read_lsdf, sparse_utils.py:35) -- to the host image of a plan.
+ *   long_threshold : folded list length from which a gene is served from the bitmap (< 0: the default,
+ *                    about 1.28 sqrt(N); 0: list rows only)
+ *   perms_per_cta  : 8, 4, 2, 1 or 0 = as many rank tables as fit one CTA's shared memory
+ *   slice_words    : 1, 2, 4 or 0 = choose by the number of bitmap rows
+ * Duplicate (gene, genome) entries -- which scipy's tocsr() at pangenome_analysis.py:75 would sum to a non-binary
+ * table -- are rejected with PGX_ERR_INVALID. */
+int pgx_host_plan_create(const int32_t *row, const int32_t *col, int64_t nnz, int32_t n_genes, int32_t n_genomes,
+                         int32_t long_threshold, int32_t perms_per_cta, int32_t slice_words, pgx_host_plan **out);
+void pgx_host_plan_destroy(pgx_host_plan *plan);
+
+/* Device plans owned by the library, on the calling thread's current device.  pgx_plan_create = pgx_host_plan_create
+ * with the defaults + pgx_plan_upload; the returned plan is what every pgx_pan_core_* call takes and lives until
+ * pgx_plan_destroy.  (A caller may instead fill a struct pgx_plan with device pointers of its own, as the Python
+ * engine can with torch tensors: the calls never look behind the struct.) */
+int pgx_plan_create(const int32_t *row, const int32_t *col, int64_t nnz, int32_t n_genes, int32_t n_genomes,
+                    int32_t long_threshold, pgx_plan **out);
+int pgx_plan_upload(const pgx_host_plan *host, pgx_plan **out);
+int pgx_plan_destroy(pgx_plan *plan);
 
 int pgx_version(void);
 const char *pgx_last_error(void);

@@ -21,7 +21,8 @@ EXPORTS = (
     "pgx_heaps_scratch_bytes", "pgx_heaps_fit", "pgx_estimate_pan_core",
     "pgx_plan_bank_order", "pgx_plan_build_bitmap", "pgx_plan_coo_to_csr", "pgx_plan_folded_lists",
     "pgx_plan_missing_genome", "pgx_plan_all_equal_u64", "pgx_plan_balance_rows", "pgx_inflate_raw",
-    "pgx_expand_deltas",
+    "pgx_expand_deltas", "pgx_host_plan_create", "pgx_host_plan_destroy", "pgx_plan_create", "pgx_plan_upload",
+    "pgx_plan_destroy",
 )
 
 
@@ -52,6 +53,43 @@ class PgxPlan(ctypes.Structure):
         ("slice_words", ctypes.c_int32),
         ("max_colsum", ctypes.c_int32),
         ("reserved_i32", ctypes.c_int32),
+    ]
+
+
+class PgxHostPlan(ctypes.Structure):
+    """Mirror of ``struct pgx_host_plan`` (include/pgx.h)."""
+    _fields_ = [
+        ("owner", ctypes.c_void_p),
+        ("chunks", ctypes.c_void_p),
+        ("tasks", ctypes.c_void_p),
+        ("sorted_idx", ctypes.c_void_p),
+        ("sorted_ptr", ctypes.c_void_p),
+        ("bits", ctypes.c_void_p),
+        ("colsum", ctypes.c_void_p),
+        ("w_present", ctypes.c_void_p),
+        ("w_absent", ctypes.c_void_p),
+        ("row_gene", ctypes.c_void_p),
+        ("row_len", ctypes.c_void_p),
+        ("row_absent", ctypes.c_void_p),
+        ("long_gene", ctypes.c_void_p),
+        ("nnz", ctypes.c_int64),
+        ("nnz_list", ctypes.c_int64),
+        ("nnz_long", ctypes.c_int64),
+        ("n_chunks", ctypes.c_int64),
+        ("n_bits_words", ctypes.c_int64),
+        ("n_sorted", ctypes.c_int64),
+        ("n_genomes", ctypes.c_int32),
+        ("n_genes", ctypes.c_int32),
+        ("n_rows", ctypes.c_int32),
+        ("n_tasks", ctypes.c_int32),
+        ("n_long", ctypes.c_int32),
+        ("n_superblocks", ctypes.c_int32),
+        ("perms_per_cta", ctypes.c_int32),
+        ("slice_words", ctypes.c_int32),
+        ("long_threshold", ctypes.c_int32),
+        ("max_colsum", ctypes.c_int32),
+        ("n_empty", ctypes.c_int32),
+        ("n_full", ctypes.c_int32),
     ]
 
 
@@ -106,6 +144,17 @@ def load():
     lib.pgx_plan_all_equal_u64.argtypes = [vp, i64, ctypes.c_uint64, i32]
     lib.pgx_inflate_raw.restype = ctypes.c_int
     lib.pgx_inflate_raw.argtypes = [vp, i64, vp, i64]
+    host_pp = ctypes.POINTER(ctypes.POINTER(PgxHostPlan))
+    lib.pgx_host_plan_create.restype = ctypes.c_int
+    lib.pgx_host_plan_create.argtypes = [vp, vp, i64, i32, i32, i32, i32, i32, host_pp]
+    lib.pgx_host_plan_destroy.restype = None
+    lib.pgx_host_plan_destroy.argtypes = [ctypes.POINTER(PgxHostPlan)]
+    lib.pgx_plan_create.restype = ctypes.c_int
+    lib.pgx_plan_create.argtypes = [vp, vp, i64, i32, i32, i32, ctypes.POINTER(plan_p)]
+    lib.pgx_plan_upload.restype = ctypes.c_int
+    lib.pgx_plan_upload.argtypes = [ctypes.POINTER(PgxHostPlan), ctypes.POINTER(plan_p)]
+    lib.pgx_plan_destroy.restype = ctypes.c_int
+    lib.pgx_plan_destroy.argtypes = [plan_p]
     lib.pgx_expand_deltas.restype = ctypes.c_int
     lib.pgx_expand_deltas.argtypes = [vp, i64, i32, vp, i32, i32]
     lib.pgx_estimate_pan_core.restype = ctypes.c_int

@@ -116,7 +116,7 @@ prep_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const Work 
     for (int g = tid; g < n; g += blockDim.x) s_rank[g] = 0xffffu;
     __syncthreads();
     for (int k = tid; k < n; k += blockDim.x) {
-        const uint32_t g = perm[k];
+        const uint32_t g = __ldg(perm + k);
         if (g < static_cast<uint32_t>(n)) s_rank[g] = static_cast<uint16_t>(k);
     }
     __syncthreads();
@@ -130,22 +130,45 @@ prep_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const Work 
     // a row that is not a permutation of 0 .. N-1 leaves a genome without a rank
     if (missing && bad_rows) atomicAdd(bad_rows, 1);
 
-    const uint32_t first = min(static_cast<uint32_t>(perm[0]), static_cast<uint32_t>(n - 1));
-    const int col_first = plan.d_colsum[first];
-    auto bin = [&](int idx) -> uint32_t {            // idx in [0, 2N)
-        const int side = idx >= n;
-        const int k = idx - side * n;
-        if (k == 0) return static_cast<uint32_t>(P16 || side == 0 ? col_first : plan.n_genes - col_first);
-        const int32_t *w_list = side == 0 ? plan.d_w_present : plan.d_w_absent;
-        const int32_t *w_other = side == 0 ? plan.d_w_absent : plan.d_w_present;
-        const uint32_t g = min(static_cast<uint32_t>(perm[k]), static_cast<uint32_t>(n - 1));
-        return static_cast<uint32_t>(w_list[g] + (k == 1 ? w_other[first] : 0));
-    };
+    // The closed forms: every bin costs a load of perm[k] and a dependent gather from a weight vector.  The loads go
+    // through the read-only path (they cannot alias the stores) and eight bins are in flight per thread.
+    const uint32_t last = static_cast<uint32_t>(n - 1);
+    const uint32_t first = min(static_cast<uint32_t>(__ldg(perm)), last);
+    const int col_first = __ldg(plan.d_colsum + first);
+    const uint32_t head_pan = __ldg(plan.d_w_absent + first), head_core = __ldg(plan.d_w_present + first);
     uint32_t *__restrict__ hist = work.hist + p * work.hist_stride;
-    if constexpr (P16) {
-        for (int w = tid; w < n; w += blockDim.x) hist[w] = bin(2 * w) | (bin(2 * w + 1) << 16);
-    } else {
-        for (int i = tid; i < 2 * n; i += blockDim.x) hist[i] = bin(i);
+    constexpr int BINS = 8;
+    for (int i0 = tid * BINS; i0 < 2 * n; i0 += blockDim.x * BINS) {
+        uint32_t g[BINS], v[BINS];
+#pragma unroll
+        for (int j = 0; j < BINS; ++j) {
+            const int idx = min(i0 + j, 2 * n - 1);
+            const int k = idx >= n ? idx - n : idx;
+            g[j] = min(static_cast<uint32_t>(__ldg(perm + k)), last);
+        }
+#pragma unroll
+        for (int j = 0; j < BINS; ++j) {
+            const int idx = min(i0 + j, 2 * n - 1);
+            v[j] = static_cast<uint32_t>(__ldg((idx >= n ? plan.d_w_absent : plan.d_w_present) + g[j]));
+        }
+#pragma unroll
+        for (int j = 0; j < BINS; ++j) {
+            const int idx = i0 + j;
+            const int side = idx >= n;
+            const int k = idx - side * n;
+            if (k == 0) v[j] = static_cast<uint32_t>(P16 || side == 0 ? col_first : plan.n_genes - col_first);
+            else if (k == 1) v[j] += side == 0 ? head_pan : head_core;
+        }
+        if constexpr (P16) {
+            // 8 bins = 4 words, 16 bytes (the rows are 4-byte aligned only: word stores)
+#pragma unroll
+            for (int j = 0; j < BINS; j += 2)
+                if (i0 + j < 2 * n) hist[(i0 + j) >> 1] = v[j] | (i0 + j + 1 < 2 * n ? v[j + 1] << 16 : 0u);
+        } else {
+#pragma unroll
+            for (int j = 0; j < BINS; ++j)
+                if (i0 + j < 2 * n) hist[i0 + j] = v[j];
+        }
     }
 }
 
@@ -554,19 +577,21 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
 // ---------------------------------------------------------------------------------------------
 // Kernel 3: histogram rows -> curves
 // ---------------------------------------------------------------------------------------------
-// One CTA per permutation: the pan half, then the core half, 2,048 bins per step with 16-byte accesses when the
+// One CTA per permutation: the pan half, then the core half, 4,096 bins per step with 16-byte accesses when the
 // genome count allows (VEC: N % 8 == 0).  The output row may BE the buffer the histogram row lives in:
 //   int32 bins:  out == hist, every bin is replaced by its curve value;
 //   packed bins: the histogram sits in the upper half of the int32 output row (bytes [4N, 8N) of 8N).  The pan half
 //                writes bytes [0, 4N) only; the core half reads bin k at byte 6N + 2k and writes curve value k at
 //                byte 4N + 4k, which stays behind every bin still to be read while k < N; all loads of a step
 //                precede its stores (the block-wide barrier of the scan), and the pan bins are dead by then.
+constexpr int SCAN_THREADS = 512;
+
 template <typename OutT, bool P16, bool VEC>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(SCAN_THREADS)
 scan_kernel(const pgx_plan plan, const Work work, OutT *out)
 {
     constexpr int ITEMS = 8;
-    constexpr int THREADS = 256;
+    constexpr int THREADS = SCAN_THREADS;
     __shared__ int warp_tot[THREADS / 32];
 
     const int n = plan.n_genomes;
@@ -574,91 +599,103 @@ scan_kernel(const pgx_plan plan, const Work work, OutT *out)
     const uint32_t *hist = work.hist + p * work.hist_stride;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
 
-    for (int side = 0; side < 2; ++side) {
-        OutT *o = out + p * 2ll * n + static_cast<long long>(side) * n;
-        int carry = 0;
-        for (int base = 0; base < n; base += THREADS * ITEMS) {
-            const int k0 = base + tid * ITEMS;
-            int v[ITEMS];
+    // bins k0 .. k0 + 7 of one side as signed steps of the curve (0 past the end)
+    auto load_bins = [&](int side, int k0, int (&v)[ITEMS]) {
 #pragma unroll
-            for (int i = 0; i < ITEMS; ++i) v[i] = 0;
-            if constexpr (P16) {
-                const uint16_t *h = reinterpret_cast<const uint16_t *>(hist) + static_cast<long long>(side) * n;
-                if constexpr (VEC) {
-                    if (k0 < n) {
-                        const uint4 a = *reinterpret_cast<const uint4 *>(h + k0);
-                        v[0] = a.x & 0xffffu; v[1] = a.x >> 16; v[2] = a.y & 0xffffu; v[3] = a.y >> 16;
-                        v[4] = a.z & 0xffffu; v[5] = a.z >> 16; v[6] = a.w & 0xffffu; v[7] = a.w >> 16;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < ITEMS; ++i) if (k0 + i < n) v[i] = h[k0 + i];
-                }
-                // packed bins hold the steps of the curve: core[k] = core[0] - (losses up to k)
-                if (side == 1) {
-#pragma unroll
-                    for (int i = 0; i < ITEMS; ++i) if (k0 + i > 0) v[i] = -v[i];
-                }
-            } else {
-                const int32_t *h = reinterpret_cast<const int32_t *>(hist) + static_cast<long long>(side) * n;
-                if constexpr (VEC) {
-                    if (k0 < n) {
-                        const int4 a = *reinterpret_cast<const int4 *>(h + k0);
-                        const int4 b = *reinterpret_cast<const int4 *>(h + k0 + 4);
-                        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
-                        v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
-                    }
-                } else {
-#pragma unroll
-                    for (int i = 0; i < ITEMS; ++i) if (k0 + i < n) v[i] = h[k0 + i];
-                }
-            }
-            int run = 0;
-#pragma unroll
-            for (int i = 0; i < ITEMS; ++i) {
-                run += v[i];
-                v[i] = run;
-            }
-            int incl = run;
-#pragma unroll
-            for (int off = 1; off < 32; off <<= 1) {
-                const int y = __shfl_up_sync(FULL_MASK, incl, off);
-                if (lane >= off) incl += y;
-            }
-            if (lane == 31) warp_tot[warp] = incl;
-            __syncthreads();                          // every load of this step has been issued and consumed
-            int before = 0, total = 0;
-#pragma unroll
-            for (int i = 0; i < THREADS / 32; ++i) {
-                const int wt = warp_tot[i];
-                if (i < warp) before += wt;
-                total += wt;
-            }
-            const int excl = carry + before + incl - run;
-#pragma unroll
-            for (int i = 0; i < ITEMS; ++i) {
-                const int c = excl + v[i];
-                // int32 bins count the genes LOST so far on the core side; packed bins are already signed steps
-                v[i] = (!P16 && side == 1) ? plan.n_genes - c : c;
-            }
+        for (int i = 0; i < ITEMS; ++i) v[i] = 0;
+        if (k0 >= n) return;
+        if constexpr (P16) {
+            const uint16_t *h = reinterpret_cast<const uint16_t *>(hist) + static_cast<long long>(side) * n;
             if constexpr (VEC) {
-                if (k0 < n) {
-                    if constexpr (sizeof(OutT) == 4) {
-                        *reinterpret_cast<int4 *>(o + k0) = make_int4(v[0], v[1], v[2], v[3]);
-                        *reinterpret_cast<int4 *>(o + k0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
-                    } else {
-#pragma unroll
-                        for (int i = 0; i < ITEMS; i += 2)
-                            *reinterpret_cast<double2 *>(o + k0 + i) = make_double2(static_cast<double>(v[i]), static_cast<double>(v[i + 1]));
-                    }
-                }
+                const uint4 a = *reinterpret_cast<const uint4 *>(h + k0);
+                v[0] = a.x & 0xffffu; v[1] = a.x >> 16; v[2] = a.y & 0xffffu; v[3] = a.y >> 16;
+                v[4] = a.z & 0xffffu; v[5] = a.z >> 16; v[6] = a.w & 0xffffu; v[7] = a.w >> 16;
             } else {
 #pragma unroll
-                for (int i = 0; i < ITEMS; ++i) if (k0 + i < n) o[k0 + i] = static_cast<OutT>(v[i]);
+                for (int i = 0; i < ITEMS; ++i) if (k0 + i < n) v[i] = h[k0 + i];
             }
-            carry += total;
-            __syncthreads();
+            // packed bins hold the steps of the curve: core[k] = core[0] - (losses up to k)
+            if (side == 1) {
+#pragma unroll
+                for (int i = 0; i < ITEMS; ++i) if (k0 + i > 0) v[i] = -v[i];
+            }
+        } else {
+            const int32_t *h = reinterpret_cast<const int32_t *>(hist) + static_cast<long long>(side) * n;
+            if constexpr (VEC) {
+                const int4 a = *reinterpret_cast<const int4 *>(h + k0);
+                const int4 b = *reinterpret_cast<const int4 *>(h + k0 + 4);
+                v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+                v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+            } else {
+#pragma unroll
+                for (int i = 0; i < ITEMS; ++i) if (k0 + i < n) v[i] = h[k0 + i];
+            }
         }
+    };
+
+    // steps (side, base) in order: the whole pan half, then the whole core half; the bins of the next step are
+    // loaded before the current one is scanned and stored (reads only ever move ahead of the writes)
+    const int chunks = (n + THREADS * ITEMS - 1) / (THREADS * ITEMS);
+    int v[ITEMS], nx[ITEMS];
+    load_bins(0, tid * ITEMS, v);
+    int carry = 0;
+    for (int step = 0; step < 2 * chunks; ++step) {
+        const int side = step >= chunks;
+        const int base = (step - side * chunks) * THREADS * ITEMS;
+        const int k0 = base + tid * ITEMS;
+        if (step + 1 < 2 * chunks) {
+            const int ns = step + 1 >= chunks;
+            load_bins(ns, (step + 1 - ns * chunks) * THREADS * ITEMS + tid * ITEMS, nx);
+        }
+        if (step == chunks) carry = 0;
+        OutT *o = out + p * 2ll * n + static_cast<long long>(side) * n;
+        int run = 0;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            run += v[i];
+            v[i] = run;
+        }
+        int incl = run;
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const int y = __shfl_up_sync(FULL_MASK, incl, off);
+            if (lane >= off) incl += y;
+        }
+        if (lane == 31) warp_tot[warp] = incl;
+        __syncthreads();                          // every load of this step (and of the next) has been issued and consumed
+        int before = 0, total = 0;
+#pragma unroll
+        for (int i = 0; i < THREADS / 32; ++i) {
+            const int wt = warp_tot[i];
+            if (i < warp) before += wt;
+            total += wt;
+        }
+        const int excl = carry + before + incl - run;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) {
+            const int c = excl + v[i];
+            // int32 bins count the genes LOST so far on the core side; packed bins are already signed steps
+            v[i] = (!P16 && side == 1) ? plan.n_genes - c : c;
+        }
+        if constexpr (VEC) {
+            if (k0 < n) {
+                if constexpr (sizeof(OutT) == 4) {
+                    *reinterpret_cast<int4 *>(o + k0) = make_int4(v[0], v[1], v[2], v[3]);
+                    *reinterpret_cast<int4 *>(o + k0 + 4) = make_int4(v[4], v[5], v[6], v[7]);
+                } else {
+#pragma unroll
+                    for (int i = 0; i < ITEMS; i += 2)
+                        *reinterpret_cast<double2 *>(o + k0 + i) = make_double2(static_cast<double>(v[i]), static_cast<double>(v[i + 1]));
+                }
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < ITEMS; ++i) if (k0 + i < n) o[k0 + i] = static_cast<OutT>(v[i]);
+        }
+        carry += total;
+#pragma unroll
+        for (int i = 0; i < ITEMS; ++i) v[i] = nx[i];
+        __syncthreads();
     }
 }
 
@@ -716,14 +753,15 @@ int device_limits(DeviceLimits *out)
     return PGX_OK;
 }
 
-// Register cap x threads of the list kernel: 1 = 48 x 1,024, 2 = 64 x 768 (the same share of the register file;
-// measured 2.5 % faster on C4).  PGX_LIST_VARIANT overrides the default.
+// Register cap x threads of the list kernel: 1 = 48 x 1,024 (default), 2 = 64 x 768 (the same share of the register
+// file).  Alone, variant 2 is 2 % faster on C4 (5.98 vs 6.09 ms per 10,000 permutations); with the probe kernel running
+// beside it -- the way every call runs -- variant 1 wins (8.33 vs 8.67 ms per step).  PGX_LIST_VARIANT overrides.
 int list_variant()
 {
     static const int v = [] {
         const char *env = getenv("PGX_LIST_VARIANT");
-        const int x = env ? atoi(env) : 2;
-        return x == 1 ? 1 : 2;
+        const int x = env ? atoi(env) : 1;
+        return x == 2 ? 2 : 1;
     }();
     return v;
 }
@@ -888,8 +926,8 @@ int launch_scan(const pgx_plan *plan, long long n_perm, const Work &work, OutT *
         // 16-byte accesses need 16-byte aligned rows: N % 8 == 0 and an aligned base
         const bool vec = n % 8 == 0 && ((reinterpret_cast<uintptr_t>(w.hist) | reinterpret_cast<uintptr_t>(d_out)) & 15) == 0 &&
                          (work.hist_stride % 4) == 0;
-        if (vec) scan_kernel<OutT, P16, true><<<grid, 256, 0, stream>>>(*plan, w, d_out + p0 * 2ll * n);
-        else scan_kernel<OutT, P16, false><<<grid, 256, 0, stream>>>(*plan, w, d_out + p0 * 2ll * n);
+        if (vec) scan_kernel<OutT, P16, true><<<grid, SCAN_THREADS, 0, stream>>>(*plan, w, d_out + p0 * 2ll * n);
+        else scan_kernel<OutT, P16, false><<<grid, SCAN_THREADS, 0, stream>>>(*plan, w, d_out + p0 * 2ll * n);
         PGX_LAUNCH_CHECK("scan_kernel");
     }
     return PGX_OK;
@@ -898,7 +936,7 @@ int launch_scan(const pgx_plan *plan, long long n_perm, const Work &work, OutT *
 // Curves of n_perm permutations: d_work is an int32 [n_perm][2N] buffer (the output itself for OutT = int32).
 template <typename OutT>
 int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, int32_t *d_work,
-               OutT *d_out, cudaStream_t stream, Aux *own_aux = nullptr)
+               OutT *d_out, cudaStream_t stream, Aux *own_aux = nullptr, int *d_bad_rows = nullptr)
 {
     if (int rc = check_plan(plan)) return rc;
     if (n_perm < 0) return fail(PGX_ERR_INVALID, "n_perm < 0");
@@ -932,8 +970,8 @@ int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, 
         work.ranks = scratch;
         work.rank_stride = n;
     }
-    int rc = p16 ? run_rows<true>(plan, d_perms, n_perm, work, nullptr, stream, own_aux, profile ? &ev : nullptr)
-                 : run_rows<false>(plan, d_perms, n_perm, work, nullptr, stream, own_aux, profile ? &ev : nullptr);
+    int rc = p16 ? run_rows<true>(plan, d_perms, n_perm, work, d_bad_rows, stream, own_aux, profile ? &ev : nullptr)
+                 : run_rows<false>(plan, d_perms, n_perm, work, d_bad_rows, stream, own_aux, profile ? &ev : nullptr);
     if (scratch) cudaFreeAsync(scratch, stream);
     if (rc) return rc;
     rc = p16 ? launch_scan<OutT, true>(plan, n_perm, work, d_out, stream)
@@ -1087,7 +1125,7 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
     std::atomic<int> failed{0};
     std::vector<std::atomic<int>> parts_done(static_cast<size_t>(n_blocks));
     for (auto &c : parts_done) c.store(0, std::memory_order_relaxed);
-    int movers = std::max(1, std::min(rng ? 6 : 12, static_cast<int>(std::thread::hardware_concurrency()) - (rng ? 3 : 2)));
+    int movers = std::max(1, std::min(rng ? 4 : 12, static_cast<int>(std::thread::hardware_concurrency()) - (rng ? 3 : 2)));
     if (const char *env = getenv("PGX_COPY_THREADS")) movers = std::max(1, std::min(32, atoi(env)));
     movers = static_cast<int>(std::max<long long>(1, std::min<long long>(movers, block * n / 32768)));
     const size_t out_elem = out_f64 ? sizeof(double) : sizeof(int32_t);
@@ -1142,9 +1180,9 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
             if (!rc && cudaMemcpyAsync(s.h_rows, s.d_hist, sizeof(uint16_t) * cnt * 2 * n, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
                 rc = fail(PGX_ERR_CUDA, "D2H copy of the curve steps failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (!rc) {
-            rc = out_f64 ? run_curves<double>(plan, s.d_perm, cnt, reinterpret_cast<int32_t *>(s.d_hist), s.d_f64, s.stream, &s.aux)
+            rc = out_f64 ? run_curves<double>(plan, s.d_perm, cnt, reinterpret_cast<int32_t *>(s.d_hist), s.d_f64, s.stream, &s.aux, d_bad_rows)
                          : run_curves<int32_t>(plan, s.d_perm, cnt, reinterpret_cast<int32_t *>(s.d_hist),
-                                               reinterpret_cast<int32_t *>(s.d_hist), s.stream, &s.aux);
+                                               reinterpret_cast<int32_t *>(s.d_hist), s.stream, &s.aux, d_bad_rows);
             const void *from = out_f64 ? static_cast<const void *>(s.d_f64) : static_cast<const void *>(s.d_hist);
             if (!rc && cudaMemcpyAsync(s.h_rows, from, out_elem * cnt * 2 * n, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
                 rc = fail(PGX_ERR_CUDA, "D2H copy of the curves failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -1166,7 +1204,7 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
         for (auto &s : buf.slot) cudaStreamSynchronize(s.stream);
         return fail(rc, "%s", text);
     }
-    if (packed && *buf.bad_rows)
+    if (*buf.bad_rows)
         return fail(PGX_ERR_INVALID, "%d of the %lld genome orders are not permutations of 0 .. %lld", *buf.bad_rows, n_perm, n - 1);
     return PGX_OK;
 }

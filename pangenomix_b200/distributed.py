@@ -27,23 +27,43 @@ def _dist():
     return dist
 
 
-def sharded_curves(perms, n_genomes, compute, device=None, group=None, dst=None):
+def _agree(ok, device, group):
+    """All ranks learn whether any of them failed before a collective that the failing rank would never join."""
+    import torch
+    dist = _dist()
+    flag = torch.tensor([0 if ok else 1], dtype=torch.int32, device=device)
+    dist.all_reduce(flag, op=dist.ReduceOp.MAX, group=group)
+    return int(flag.item()) == 0
+
+
+def sharded_curves(perms, n_genomes, compute=None, device=None, group=None, dst=None, engine=None):
     """Rarefies ``perms`` ([num_iter, N] uint16, significant on rank 0 only) across the group.
 
-    compute : callable(numpy uint16 [k, N]) -> numpy int32 [k, 2N] on this rank's GPU
+    engine  : a PanCoreEngine on this rank's GPU -- the permutation table is broadcast on the device, every rank
+              rarefies its contiguous block with ``curves_device`` and the int32 blocks are gathered on the device
+              (NCCL over NVLink); nothing but rank 0's permutations and the final table crosses PCIe.
+    compute : instead of an engine, callable(numpy uint16 [k, N]) -> numpy int32 [k, 2N] (the CPU tests of this
+              host-side logic inject one; tensors then live on ``device``, the CPU by default).
     dst     : None -> every rank returns the full table (all_gather);
               r    -> only rank r returns it (gather), the others return None.
     """
     import torch
     dist = _dist()
     world, rank = dist.get_world_size(group), dist.get_rank(group)
+    if engine is not None:
+        device = engine.device
     device = torch.device("cpu") if device is None else torch.device(device)
 
-    shape = torch.zeros(1, dtype=torch.int64, device=device)
+    # rank 0 validates before anybody enters a collective the others could hang in
+    problem = None
     if rank == 0:
         perms = np.ascontiguousarray(perms, dtype=np.uint16)
         if perms.ndim != 2 or perms.shape[1] != n_genomes:
-            raise ValueError("perms must have shape [num_iter, %d]" % n_genomes)
+            problem = "perms must have shape [num_iter, %d]" % n_genomes
+    if not _agree(problem is None, device, group):
+        raise ValueError(problem or "rank 0 rejected the permutation table")
+    shape = torch.zeros(1, dtype=torch.int64, device=device)
+    if rank == 0:
         shape[0] = perms.shape[0]
     dist.broadcast(shape, src=0, group=group)
     num_iter = int(shape.item())
@@ -56,17 +76,17 @@ def sharded_curves(perms, n_genomes, compute, device=None, group=None, dst=None)
         dist.broadcast(table.view(torch.uint8), src=0, group=group)
 
     lo, hi = shard_bounds(num_iter, world, rank)
-    mine = table[lo:hi].cpu().numpy().view(np.uint16)
-    local = compute(mine) if hi > lo else np.zeros((0, 2 * n_genomes), dtype=np.int32)
-    local = np.ascontiguousarray(local, dtype=np.int32)
-    if local.shape != (hi - lo, 2 * n_genomes):
-        raise ValueError("compute returned shape %s, expected %s" % (local.shape, (hi - lo, 2 * n_genomes)))
-
     # equal-sized padded blocks so a single (all_)gather moves everything
     width = shard_bounds(num_iter, world, 0)[1]
     block = torch.zeros((max(width, 1), 2 * n_genomes), dtype=torch.int32, device=device)
     if hi > lo:
-        block[:hi - lo].copy_(torch.from_numpy(local))
+        if engine is not None:
+            engine.curves_device(table[lo:hi], out=block[:hi - lo])
+        else:
+            local = np.ascontiguousarray(compute(table[lo:hi].cpu().numpy().view(np.uint16)), dtype=np.int32)
+            if local.shape != (hi - lo, 2 * n_genomes):
+                raise ValueError("compute returned shape %s, expected %s" % (local.shape, (hi - lo, 2 * n_genomes)))
+            block[:hi - lo].copy_(torch.from_numpy(local))
     if dst is None:
         gathered = torch.empty((world * block.shape[0], block.shape[1]), dtype=torch.int32, device=device)
         dist.all_gather_into_tensor(gathered, block, group=group)
@@ -84,25 +104,23 @@ def sharded_curves(perms, n_genomes, compute, device=None, group=None, dst=None)
     return out
 
 
-def estimate_pan_core_size_sharded(df_genes, num_iter, log_batch=-1, group=None, dst=None, compute=None):
+def estimate_pan_core_size_sharded(df_genes, num_iter, log_batch=-1, group=None, dst=None, compute=None, engine=None):
     """Multi-GPU ``estimate_pan_core_size``: same DataFrame as the single-GPU call on the
     ranks that receive it (all ranks for ``dst=None``), None elsewhere.
 
-    Every rank must call it with the same table; only rank 0's numpy RNG is consumed.
-    ``compute`` is injectable for the CPU tests of the sharding logic; by default each rank
-    runs the CUDA engine on its own device.
+    Every rank must call it with the same table; only rank 0's numpy RNG is consumed (exactly ``num_iter``
+    legacy shuffles, as pangenome_analysis.py:84-85).  Each rank plans and uploads the table once per LSDF
+    object (the engine cache of the single-GPU call) unless an ``engine`` is passed.  ``compute`` is injectable
+    for the CPU tests of the sharding logic.
     """
     import pandas as pd
-    import torch
-    from .engine import PanCoreEngine, draw_legacy_permutations
+    from .engine import draw_legacy_permutations
     dist = _dist()
     rank = dist.get_rank(group)
     num_genes, num_strains = df_genes.shape
-    device = None
-    if compute is None:
-        engine = PanCoreEngine(df_genes.data)
-        device = engine.device
-        compute = engine.curves_host
+    if compute is None and engine is None:
+        from .pangenome_analysis import _engine_for
+        engine = _engine_for(df_genes)
     perms = None
     if rank == 0:
         print('Converting DataFrame to matrix...')
@@ -111,7 +129,7 @@ def estimate_pan_core_size_sharded(df_genes, num_iter, log_batch=-1, group=None,
             for it in range(log_batch, num_iter + 1, log_batch):
                 print('\tIteration', it, 'of', num_iter)
         perms = draw_legacy_permutations(num_strains, num_iter)
-    curves = sharded_curves(perms, num_strains, compute, device=device, group=group, dst=dst)
+    curves = sharded_curves(perms, num_strains, compute, group=group, dst=dst, engine=engine)
     if curves is None:
         return None
     iter_index = ['Iter' + str(x) for x in range(1, num_iter + 1)]
@@ -122,6 +140,10 @@ def estimate_pan_core_size_sharded(df_genes, num_iter, log_batch=-1, group=None,
 
 class CurveGather:
     """Gathers every rank's int32 curve block of a step on rank ``dst`` over NVLink.
+
+    Contract: buffer b may be sent again only after the destination has consumed its previous content; callers
+    reuse a buffer after a barrier or a drain on every rank (bench.py alternates two buffers per step and reads the
+    gathered blocks only behind a barrier) -- there is no cross-rank flow control inside the class.
 
     Preferred path: peer memory.  The destination is a symmetric-memory buffer
     (torch.distributed._symmetric_memory: cuMem allocations mapped into every peer over
@@ -159,6 +181,13 @@ class CurveGather:
             except Exception as exc:                                   # noqa: BLE001 - any failure means "no peer path"
                 self._peer = None
                 self.fallback_reason = "%s: %s" % (type(exc).__name__, exc)
+        if prefer_peer and self.device.type == "cuda" and self.world > 1:
+            # the mode is a collective decision: a rank pushing into peer memory while another waits in
+            # dist.gather would deadlock the group
+            if not _agree(self._peer is not None, self.device, group) and self._peer is not None:
+                self._peer = None
+                self.mode = "nccl-gather"
+                self.fallback_reason = "another rank could not map the symmetric buffer"
         if self._peer is None and self.rank == self.dst:
             self._lists = [[torch.empty((self.rows, self.width), dtype=torch.int32, device=self.device)
                             for _ in range(self.world)] for _ in range(self.n_buffers)]

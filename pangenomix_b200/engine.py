@@ -96,27 +96,43 @@ class PanCoreEngine:
         hp = self.host_plan
         self.n_genes, self.n_genomes = hp.n_genes, hp.n_genomes
 
-        def up(arr, as_dtype):
-            flat = np.ascontiguousarray(arr).view(as_dtype).reshape(-1)
-            if flat.size == 0:
-                return torch.zeros(4, dtype=torch.from_numpy(flat).dtype, device=self.device)
-            return torch.from_numpy(flat).to(self.device)
+        # the device copy is made and owned by the library (pgx_plan_upload / pgx_plan_destroy)
+        with torch.cuda.device(self.device):
+            self._plan_ptr = self._upload(hp)
+        self.c_plan = self._plan_ptr.contents
 
-        self._buffers = {
-            "chunks": up(hp.chunks, np.int16), "tasks": up(hp.tasks, np.int32),
-            "sorted_idx": up(hp.sorted_idx, np.int16), "sorted_ptr": up(hp.sorted_ptr, np.int32),
-            "bits": up(hp.bits, np.int32),
-            "colsum": up(hp.colsum, np.int32), "w_present": up(hp.w_present, np.int32),
-            "w_absent": up(hp.w_absent, np.int32)}
-        ptr = {k: v.data_ptr() for k, v in self._buffers.items()}
-        self.c_plan = _native.PgxPlan(
-            d_chunks=ptr["chunks"], d_tasks=ptr["tasks"], d_sorted_idx=ptr["sorted_idx"],
-            d_sorted_ptr=ptr["sorted_ptr"], d_bits=ptr["bits"], reserved_ptr=None,
-            d_colsum=ptr["colsum"], d_w_present=ptr["w_present"], d_w_absent=ptr["w_absent"],
-            n_chunks=hp.n_chunks, n_genomes=hp.n_genomes, n_genes=hp.n_genes,
-            n_rows=hp.n_rows, n_tasks=hp.n_tasks, n_long=hp.n_long,
-            n_superblocks=hp.n_superblocks, perms_per_cta=hp.perms_per_cta, slice_words=hp.slice_words,
-            max_colsum=int(hp.colsum.max()) if hp.colsum.size else 0, reserved_i32=0)
+    def _upload(self, hp):
+        if hp.c_owner is not None:                       # the library's own planner made it: upload its image
+            host = hp.c_owner.pointer
+        else:                                            # numpy specification (tests, unusual tables): wrap the arrays
+            keep = [np.ascontiguousarray(a) for a in (
+                hp.chunks, hp.tasks, hp.sorted_idx, hp.sorted_ptr, hp.bits, hp.colsum, hp.w_present, hp.w_absent)]
+            ptr = [a.ctypes.data if a.size else None for a in keep]
+            image = _native.PgxHostPlan(
+                owner=None, chunks=ptr[0], tasks=ptr[1], sorted_idx=ptr[2], sorted_ptr=ptr[3], bits=ptr[4],
+                colsum=ptr[5], w_present=ptr[6], w_absent=ptr[7], row_gene=None, row_len=None, row_absent=None,
+                long_gene=None, nnz=hp.nnz, nnz_list=hp.nnz_list, nnz_long=hp.nnz_long, n_chunks=hp.n_chunks,
+                n_bits_words=int(hp.bits.size), n_sorted=int(hp.sorted_idx.size), n_genomes=hp.n_genomes,
+                n_genes=hp.n_genes, n_rows=hp.n_rows, n_tasks=hp.n_tasks, n_long=hp.n_long,
+                n_superblocks=hp.n_superblocks, perms_per_cta=hp.perms_per_cta, slice_words=hp.slice_words,
+                long_threshold=hp.long_threshold, max_colsum=int(hp.colsum.max()) if hp.colsum.size else 0,
+                n_empty=hp.n_empty, n_full=hp.n_full)
+            host = ctypes.pointer(image)
+        out = ctypes.POINTER(_native.PgxPlan)()
+        _native.check(self.lib.pgx_plan_upload(host, ctypes.byref(out)))
+        return out
+
+    def close(self):
+        """Frees the device copy of the table (also done when the engine is garbage-collected)."""
+        ptr, self._plan_ptr = getattr(self, "_plan_ptr", None), None
+        if ptr:
+            self.lib.pgx_plan_destroy(ptr)
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:                                # noqa: BLE001 - interpreter shutdown
+            pass
 
     # ---- device-resident path -------------------------------------------------------
     def curves_device(self, perms, out=None):

@@ -100,6 +100,7 @@ class HostPlan:
     long_gene: np.ndarray     # int64  [n_long]
     nnz_list: int = 0         # present entries of the list-row genes (roofline apportioning)
     nnz_long: int = 0         # present entries of the bitmap-row genes
+    c_owner: object = None    # keeps the library's host image alive when the arrays above are views of it
 
     @property
     def n_rows(self):
@@ -532,9 +533,93 @@ def _bank_ordered_chunks(flat, ptr, block_first, block_nch, block_first_row, blo
     return chunks
 
 
+class _CHostPlan:
+    """Owner of a ``pgx_host_plan`` made by the library's planner (freed with the last HostPlan that views it)."""
+
+    def __init__(self, pointer, destroy):
+        self.pointer = pointer
+        self._destroy = destroy                  # bound now: module globals may be gone at interpreter shutdown
+
+    def __del__(self):
+        if self.pointer is not None:
+            self._destroy(self.pointer)
+            self.pointer = None
+
+
+def _library_plan(data, long_threshold, perms_per_cta, slice_words):
+    """The whole plan from the library's own planner (pgx_host_plan_create, csrc/pgx_plan_build.cpp) for the usual
+    input -- a COO matrix whose stored values are all 1; None when the table needs the specification's handling
+    (other formats or values, duplicate entries, empty tables)."""
+    import ctypes
+    from . import _native
+    if not (scipy.sparse.issparse(data) and data.format == "coo" and data.ndim == 2
+            and 0 < data.shape[1] <= MAX_GENOMES and data.shape[0] < 2 ** 31 - 1 and data.nnz > 0):
+        return None
+    lib = _native.load()
+    values = np.asarray(data.data)
+    if values.dtype in (np.dtype(np.int64), np.dtype(np.float64)) and values.flags.c_contiguous:
+        one = 1 if values.dtype == np.dtype(np.int64) else int(np.float64(1.0).view(np.uint64))
+        all_ones = bool(lib.pgx_plan_all_equal_u64(values.ctypes.data, values.shape[0], one, 0))
+    else:
+        all_ones = values.dtype != object and bool(np.all(values == 1))
+    if not all_ones:
+        return None
+    n_genes, n = (int(v) for v in data.shape)
+    row = np.ascontiguousarray(data.row, dtype=np.int32)
+    col = np.ascontiguousarray(data.col, dtype=np.int32)
+    if row.size and (row.min() < 0 or row.max() >= n_genes or col.min() < 0 or col.max() >= n):
+        raise ValueError("COO indices out of range")
+    out = ctypes.POINTER(_native.PgxHostPlan)()
+    rc = lib.pgx_host_plan_create(row.ctypes.data, col.ctypes.data, int(row.shape[0]), n_genes, n,
+                                  -1 if long_threshold is None else int(long_threshold),
+                                  0 if perms_per_cta is None else int(perms_per_cta),
+                                  0 if slice_words is None else int(slice_words), ctypes.byref(out))
+    if rc != 0:
+        message = lib.pgx_last_error().decode("utf-8", "replace")
+        if "duplicate" in message:
+            return None                      # let the specification decide (duplicates sum to 2 -> rejected)
+        _native.check(rc)
+    owner = _CHostPlan(out, lib.pgx_host_plan_destroy)
+    h = out.contents
+
+    def view(ptr, count, dtype):
+        count = int(count)
+        if count == 0 or not ptr:
+            return np.zeros(0, dtype=dtype)
+        buf = (ctypes.c_char * (count * np.dtype(dtype).itemsize)).from_address(ptr)
+        arr = np.frombuffer(buf, dtype=dtype, count=count)
+        arr.flags.writeable = False
+        return arr
+
+    return HostPlan(
+        n_genes=int(h.n_genes), n_genomes=int(h.n_genomes), nnz=int(h.nnz), perms_per_cta=int(h.perms_per_cta),
+        long_threshold=int(h.long_threshold),
+        colsum=view(h.colsum, h.n_genomes, np.int32), w_present=view(h.w_present, h.n_genomes, np.int32),
+        w_absent=view(h.w_absent, h.n_genomes, np.int32), n_empty=int(h.n_empty), n_full=int(h.n_full),
+        chunks=view(h.chunks, h.n_chunks * CHUNK, np.uint16), tasks=view(h.tasks, h.n_tasks * 4, np.int32).reshape(-1, 4),
+        sorted_idx=view(h.sorted_idx, h.n_sorted, np.uint16), sorted_ptr=view(h.sorted_ptr, h.n_rows + 1, np.int32),
+        row_gene=view(h.row_gene, h.n_rows, np.int64), row_len=view(h.row_len, h.n_rows, np.int32),
+        row_absent=view(h.row_absent, h.n_rows, np.uint8).astype(bool),
+        bits=view(h.bits, h.n_bits_words, np.uint32), slice_words=int(h.slice_words),
+        long_gene=view(h.long_gene, h.n_long, np.int64), nnz_list=int(h.nnz_list), nnz_long=int(h.nnz_long),
+        c_owner=owner)
+
+
 def build_host_plan(data, long_threshold=None, perms_per_cta=None, slice_words=None) -> HostPlan:
+    """The plan of a table.  The library's own planner (pgx_host_plan_create) does the whole job for the usual
+    input; PGX_PLAN_PYTHON=1 runs the orchestration below with the library's per-step host helpers instead, and
+    PGX_PLAN_NUMPY=1 the pure numpy / scipy specification of every step (the three are bit-identical, tested)."""
+    import os
     if scipy.sparse.issparse(data) and data.ndim == 2 and data.shape[1] > MAX_GENOMES:
         raise ValueError("n_genomes = %d exceeds the supported maximum of %d" % (data.shape[1], MAX_GENOMES))
+    if not _numpy_spec() and os.environ.get("PGX_PLAN_PYTHON") != "1":
+        if perms_per_cta is not None and perms_per_cta not in (1, 2, 4, 8):
+            raise ValueError("perms_per_cta must be 1, 2, 4 or 8")
+        if slice_words is not None and int(slice_words) not in (1, 2, 4):
+            raise ValueError("slice_words must be 1, 2 or 4")
+        plan = _library_plan(data, long_threshold, perms_per_cta, slice_words)
+        if plan is not None:
+            return plan
     indptr, indices, colsum, (n_genes, n) = canonical_csr(data)
     nnz = int(indices.shape[0])
     if n < 1:
@@ -647,6 +732,8 @@ def build_host_plan(data, long_threshold=None, perms_per_cta=None, slice_words=N
         chunks = np.zeros(0, dtype=np.uint16)
         tasks = np.zeros((0, 4), dtype=np.int32)
 
+    if long_threshold < 0:
+        raise ValueError("long_threshold must be >= 0 (0: list rows only)")
     return HostPlan(
         n_genes=int(n_genes), n_genomes=int(n), nnz=nnz,
         perms_per_cta=int(perms_per_cta), long_threshold=long_threshold,

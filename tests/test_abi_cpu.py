@@ -212,3 +212,24 @@ def test_expand_deltas_rebuilds_the_curves(n, rows, f64):
     big[0, 0] = big[0, n] = 65535
     _native.check(_native.load().pgx_expand_deltas(big.ctypes.data, 1, n, out.ctypes.data, f64, 1))
     assert out[0, 0] == 65535 and out[0, n - 1] == 65535 and out[0, 2 * n - 1] == 65535
+
+
+def _build_c_host(tmp_path):
+    import subprocess
+    exe = str(tmp_path / "abi_host")
+    lib_dir = os.path.join(REPO, "pangenomix_b200")
+    subprocess.run(["gcc", "-O2", "-I", os.path.join(REPO, "include"), os.path.join(REPO, "tests", "c", "abi_host.c"),
+                    "-L", lib_dir, "-lpgx_b200", "-Wl,-rpath," + lib_dir, "-o", exe], check=True)
+    return exe
+
+
+def test_c_host_links_only_the_library_and_plans_a_table(tmp_path):
+    """tests/c/abi_host.c: a plain C program against include/pgx.h and libpgx_b200.so alone (no Python in the loop)
+    plans a table with pgx_host_plan_create; its GPU half runs in tests/test_gpu_parity.py."""
+    import subprocess
+    _native.load()
+    exe = _build_c_host(tmp_path)
+    out = subprocess.run([exe], check=True, capture_output=True, text=True).stdout
+    assert "host ok" in out and "bitmap rows" in out
+    needed = subprocess.run(["ldd", exe], check=True, capture_output=True, text=True).stdout
+    assert "libpgx_b200.so" in needed and "python" not in needed.lower() and "torch" not in needed.lower()

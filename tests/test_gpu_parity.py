@@ -387,6 +387,17 @@ def test_genomes_above_65535_genes_use_int32_bins(engine_mod):
     assert np.array_equal(eng.estimate(21), want.astype(np.float64))
 
 
+def test_c_host_program_end_to_end(engine_mod, tmp_path):
+    """tests/c/abi_host.c --gpu: plan, upload, rarefy and check 21 genome orders from plain C through the C ABI alone
+    (pgx_host_plan_create, pgx_plan_upload, pgx_pan_core_curves_host, pgx_plan_create, pgx_plan_destroy)."""
+    import subprocess
+    from test_abi_cpu import _build_c_host
+    exe = _build_c_host(tmp_path)
+    run = subprocess.run([exe, "--gpu"], capture_output=True, text=True)
+    assert run.returncode == 0, run.stdout + run.stderr
+    assert "gpu ok: 21 curves bit-exact" in run.stdout
+
+
 def test_rows_that_are_not_permutations_are_reported(engine_mod):
     from pangenomix_b200 import _native
     coo = _mixed_matrix(300)

@@ -274,3 +274,44 @@ def test_plan_wide_table_two_permutations_per_cta_with_row_balance():
     perms = np.stack([rng.permutation(50000) for _ in range(2)])
     pan, core = cport.curves_direct(coo, perms.astype(np.int32), n_threads=2)
     assert np.array_equal(curves_from_plan(hp, perms), np.hstack([pan, core]).astype(np.int64))
+
+
+@pytest.mark.parametrize("name", ["c1", "c2"])
+def test_three_planners_agree(monkeypatch, name):
+    """The library's own planner (pgx_host_plan_create, what a C host gets), the Python orchestration over the
+    library's per-step helpers (PGX_PLAN_PYTHON=1) and the numpy / scipy specification (PGX_PLAN_NUMPY=1): the same
+    plan, array by array, on configs C1 and C2."""
+    from conftest import config_matrix_cached
+    from pangenomix_b200 import synth
+    coo = synth.config_matrix("c1") if name == "c1" else config_matrix_cached("c2")
+    library = build_host_plan(coo)
+    assert library.c_owner is not None and library.n_long > 0 and library.n_rows > 0
+    monkeypatch.setenv("PGX_PLAN_PYTHON", "1")
+    helpers = build_host_plan(coo)
+    monkeypatch.delenv("PGX_PLAN_PYTHON")
+    monkeypatch.setenv("PGX_PLAN_NUMPY", "1")
+    spec = build_host_plan(coo)
+    monkeypatch.delenv("PGX_PLAN_NUMPY")
+    assert helpers.c_owner is None and spec.c_owner is None
+    _plans_equal(library, spec)
+    _plans_equal(helpers, spec)
+    for f in ("n_empty", "n_full", "nnz", "nnz_list", "nnz_long", "long_threshold", "perms_per_cta", "slice_words"):
+        assert getattr(library, f) == getattr(spec, f), f
+    assert np.array_equal(library.row_gene, spec.row_gene) and np.array_equal(library.long_gene, spec.long_gene)
+    assert np.array_equal(library.row_len, spec.row_len) and np.array_equal(library.row_absent, spec.row_absent)
+
+
+def test_library_planner_options_and_errors():
+    x = _mixed_matrix(900, seed=2, per_class=60)
+    coo = scipy.sparse.coo_matrix(x)
+    lists_only = build_host_plan(coo, long_threshold=0)
+    assert lists_only.c_owner is not None and lists_only.n_long == 0 and lists_only.bits.size == 0
+    assert build_host_plan(coo).long_threshold == 38             # round(1.28 sqrt(900)), as the specification
+    with pytest.raises(ValueError):
+        build_host_plan(coo, perms_per_cta=3)
+    with pytest.raises(ValueError):
+        build_host_plan(coo, slice_words=3)
+    bad = scipy.sparse.coo_matrix((np.ones(2, dtype=np.int64), ([0, 1], [0, 0])), shape=(3, 2))
+    bad.row[1] = 5                                              # gene index outside the table
+    with pytest.raises(ValueError):
+        build_host_plan(bad)
