@@ -17,11 +17,12 @@ configuration the north_star's roofline and scaling targets are quoted on.
           asynchronously, overlapped with the next step; NCCL gather as fallback).
   e2e   : the same through the host-buffer C-ABI call (pinned host permutations in,
           host curves out; copies inside the timed region).
-  roofline : the slower of the two row kernels against ITS share of the algorithmic bytes of
-          SURVEY.md section 8d (4 nnz + 4 (G + 1) per permutation for the whole table), over its
-          CUDA-event duration (a separate pass: the timed region runs the two kernels side by
-          side), against the measured HBM copy bandwidth of MEASURED_PEAKS.json; traffic = DRAM
-          bytes of that kernel from the committed ncu capture (profiles/roofline_traffic.json).
+  roofline : the slower of the two row kernels against the pipe that binds it -- the list kernel against
+          the shared-memory / LSU data pipe (wavefronts from the committed ncu capture x 128 B over its live
+          CUDA-event duration, a separate pass: the timed region runs the two kernels side by side), the
+          probe kernel against instruction issue; SURVEY.md section 8d's HBM bookkeeping (4 nnz + 4 (G + 1)
+          algorithmic bytes per permutation, measured HBM copy peak of MEASURED_PEAKS.json, DRAM bytes
+          from ncu) is kept under roofline.hbm as an EFFECTIVE fraction.
   cpu_baseline : the oracle's C port of the reference algorithm on a bounded sample.
   api   : the reference-facing Python call itself, estimate_pan_core_size(df, 2000): host RNG
           stream + H2D + kernels + D2H + float64 DataFrame.
@@ -67,6 +68,8 @@ def parse_args():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="budget of the cpu_baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--cpu-check", action="store_true",
+                    help="N > 1: rank 0 also runs the cpu_baseline leg (oracle check of its GPU curves) while the others wait")
     ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
                     help="weak (default, what the driver runs): every GPU rarefies the config's permutation count; "
                          "strong: the config's permutations are split over the GPUs, as BASELINE.json words C4")
@@ -126,6 +129,37 @@ def cpu_sample(coo, n_genomes, budget_s, threads):
     return gm, perms, t1
 
 
+def python_reference_sample(coo, eng=None, n_iter=1):
+    """The UNMODIFIED Python reference (vendored into git-ignored baseline/_ref by baseline/vendor_ref.py) on
+    ``n_iter`` permutations of the same table: its own estimate_pan_core_size, one host core as the reference runs.
+    With an engine, the GPU curves of the same seed are checked against the reference's output bit for bit."""
+    try:
+        from baseline import vendor_ref
+        ref_pa, ref_su = vendor_ref.import_reference()
+    except ImportError as exc:
+        return {"unavailable": str(exc)}
+    import contextlib
+    import io
+    from pangenomix_b200 import synth
+    index, columns = synth.labels_for(*coo.shape)
+    lsdf = ref_su.LightSparseDataFrame(index, columns, coo)
+    np.random.seed(12345)
+    t0 = time.perf_counter()
+    with contextlib.redirect_stdout(io.StringIO()):
+        df = ref_pa.estimate_pan_core_size(lsdf, n_iter)
+    dt = time.perf_counter() - t0
+    out = {"value": n_iter / dt, "unit": UNIT, "cores": 1, "kind": "reference", "seconds": dt,
+           "sample": "%d permutation(s) of the same table through the reference's own estimate_pan_core_size "
+                     "(pangenome_analysis.py:51-98, numpy %s), incl. its COO -> CSR conversion" % (n_iter, np.__version__)}
+    if eng is not None:
+        from pangenomix_b200 import engine
+        np.random.seed(12345)
+        perms = engine.draw_legacy_permutations(coo.shape[1], n_iter)
+        out["gpu_curves_equal_reference"] = bool(np.array_equal(eng.curves_host(perms, out_f64=True), df.values))
+        assert out["gpu_curves_equal_reference"], "GPU != Python reference"
+    return out
+
+
 def run_reference(args, rank, world):
     if rank != 0:
         return
@@ -152,7 +186,8 @@ def run_reference(args, rank, world):
         "data": "synthetic", "config": workload_config(args.workload, coo, perms_cfg, world),
         "cells_per_s": value * coo.shape[0] * coo.shape[1],
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "single_thread_s_per_perm": t1},
+                         "single_thread_s_per_perm": t1,
+                         "reference_python": python_reference_sample(coo, None, n_iter=1 if coo.shape[1] >= 2000 else 20)},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -223,15 +258,15 @@ def measured_peak():
         return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md)"
 
 
-def ncu_traffic(workload, kind, perms):
-    """DRAM bytes per launch of the dominant row kernel, scaled from the committed ncu capture
-    (profiles/roofline_traffic.json holds dram bytes per permutation), if there is one."""
+def ncu_counters(workload, kind):
+    """Per-permutation counters of a kernel from the committed ncu capture (profiles/roofline_traffic.json, written
+    by scripts/ncu_summary.py from the ``ncu --set full`` report of the same workload): DRAM bytes, LSU wavefronts,
+    pipe utilisations.  Empty when nothing is committed for this workload."""
     try:
         with open(os.path.join(REPO, "profiles", "roofline_traffic.json")) as f:
-            per_perm = json.load(f)[workload][kind]["dram_bytes_per_perm"]
-        return float(per_perm) * perms
+            return dict(json.load(f)[workload][kind])
     except (OSError, ValueError, KeyError, TypeError):
-        return None
+        return {}
 
 
 # --------------------------------------------------------------------------------------
@@ -277,9 +312,13 @@ def run_b200(args, rank, world, local_rank):
 
     # every rank rarefies its own permutations (numpy legacy stream, seed 12345 + rank)
     h_perms, h_perms_owner = engine.pinned_empty((perms_n, n), np.uint16)
-    np.random.seed(12345 + rank)
     t = time.time()
-    engine.draw_legacy_permutations(n, perms_n, out=h_perms)
+    if args.scaling == "strong":
+        np.random.seed(12345)                     # ONE stream, sharded in contiguous blocks like the multi-GPU API
+        h_perms[:] = engine.draw_legacy_permutations(n, perms_total)[lo:hi]
+    else:
+        np.random.seed(12345 + rank)
+        engine.draw_legacy_permutations(n, perms_n, out=h_perms)
     host_rng_s = time.time() - t
     d_perms = torch.empty((perms_n, n), dtype=torch.int16, device=device)
     d_perms.copy_(h_perms_owner)
@@ -443,13 +482,31 @@ def run_b200(args, rank, world, local_rank):
         t0 = time.perf_counter()
         engine.draw_legacy_permutations(n, iters)
         rng_s = time.perf_counter() - t0
+        # the first call on a table a user has on disk: read_lsdf (inflate + labels) + plan + upload + curves
+        import tempfile
+        npz = os.path.join(tempfile.gettempdir(), "pgx_bench_%s.npz" % args.workload)
+        if not os.path.exists(npz):
+            lsdf.to_npz(npz)
+        t0 = time.perf_counter()
+        cold = su.read_lsdf(npz)
+        t_read = time.perf_counter() - t0
+        np.random.seed(12345)
+        with contextlib.redirect_stdout(io.StringIO()):
+            df_cold = pa.estimate_pan_core_size(cold, 64)
+        t_cold = time.perf_counter() - t0
+        assert np.array_equal(df_cold.values, df.values[:64])
+        api_cold = {"call": "read_lsdf(npz) + estimate_pan_core_size(df_genes, 64) on a table not seen before",
+                    "seconds": t_cold, "read_lsdf_seconds": t_read, "plan_upload_first_call_seconds": t_cold - t_read,
+                    "npz_bytes": os.path.getsize(npz)}
+        del cold, df_cold
         assert df.shape == (iters, 2 * n) and df.values.dtype == np.float64
         assert np.array_equal(df.values[:8].astype(np.int32), h_check[:8]) if iters >= 8 else True
         api = {"call": "pangenomix_b200.pangenome_analysis.estimate_pan_core_size(df_genes, %d)" % iters,
                "value": iters / api_s, "unit": UNIT, "seconds": api_s,
                "host_rng_seconds": rng_s, "host_rng_perms_per_s": iters / rng_s,
                "note": "includes the %d numpy-legacy shuffles drawn on the host (bit-exact RNG stream), "
-                       "H2D/D2H and the float64 DataFrame; the table was already resident" % iters}
+                       "H2D/D2H and the float64 DataFrame; the table was already resident" % iters,
+               "cold": api_cold}
         del df
 
     # ---- next row of the scope table: Heaps-law fits of every curve of the step, on the device ----
@@ -490,34 +547,64 @@ def run_b200(args, rank, world, local_rank):
     peak, peak_src = measured_peak()
     a_perm = hp.algorithmic_bytes_per_perm
     calls = max(1, calls)
-    # dominant kernel: the slower of the two row kernels, against ITS share of the algorithmic bytes
+    # dominant kernel: the slower of the two row kernels
     kind = "list" if list_ms >= probe_ms else "probe"
     k_ms = (list_ms if kind == "list" else probe_ms) / calls
     k_bytes = hp.algorithmic_bytes_of(kind)
-    achieved = k_bytes * perms_n / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
+    hbm_achieved = k_bytes * perms_n / (k_ms / 1e3) / 1e9 if k_ms > 0 else None
     combined = a_perm * perms_n / (row_ms / calls / 1e3) / 1e9 if row_ms > 0 else None
-    traffic = ncu_traffic(args.workload, kind, perms_n)
-    roofline = {
-        "bound": "hbm", "kernel": "list_kernel<%d>" % hp.perms_per_cta if kind == "list" else "probe_kernel",
-        "achieved": achieved, "peak": peak, "unit": "GB/s",
-        "frac": achieved / peak if achieved else None, "traffic": traffic, "peak_source": peak_src,
-        "algorithmic_bytes_per_perm": k_bytes, "algorithmic_bytes_per_perm_whole_table": a_perm,
+    ncu = ncu_counters(args.workload, kind)
+    sm_mhz = (clocks or {}).get("sm_mhz") or 1965.0
+    sm_count = int(_native.device_info()["sm_count"])
+    kernel_name = "list_kernel<%d>" % hp.perms_per_cta if kind == "list" else "probe_kernel<%d>" % hp.slice_words
+    if kind == "list":
+        # What binds the list kernel is the shared-memory / LSU data pipe of the SMs (one 128-byte wavefront per
+        # clock per SM), not HBM: every folded index is ONE shared-memory gather of 2 bytes per permutation.
+        smem_peak = 128.0 * sm_count * sm_mhz * 1e6 / 1e9
+        wf = ncu.get("lsu_wavefronts_per_perm")
+        achieved = wf * 128.0 * perms_n / (k_ms / 1e3) / 1e9 if wf and k_ms > 0 else None
+        roofline = {
+            "bound": "smem_lsu", "kernel": kernel_name, "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
+            "frac": achieved / smem_peak if achieved else None,
+            "traffic": wf * 128.0 * perms_n if wf else None,
+            "peak_source": "128 B per clock per SM x %d SMs x %.0f MHz (SM clock sampled during the timed region)" % (sm_count, sm_mhz),
+            "pipe_utilisation_under_ncu": (ncu.get("lsu_pipe_pct_of_peak") or 0) / 100.0 or None,
+            "wavefronts_per_lds128": ncu.get("wavefronts_per_shared_load"),
+            "algorithmic_smem_bytes_per_perm": 2 * hp.folded_nnz,
+            "algorithmic_frac": 2.0 * hp.folded_nnz * perms_n / (k_ms / 1e3) / 1e9 / smem_peak if k_ms > 0 else None,
+            "note": "achieved = LSU data-pipe wavefronts of the kernel (ncu capture at HEAD, %s) x 128 B / live CUDA-event "
+                    "duration; the wavefronts are shared-memory gathers (one LDS.128 per folded index per %d permutations), "
+                    "histogram REDs, chunk loads and rank-table stores; algorithmic_frac counts only 2 bytes per (folded index, "
+                    "permutation)" % (ncu.get("source", "none committed"), hp.perms_per_cta),
+        }
+    else:
+        issue = (ncu.get("issue_active_pct") or 0) / 100.0 or None
+        roofline = {
+            "bound": "issue", "kernel": kernel_name, "achieved": issue, "peak": 1.0, "unit": "fraction of issue slots",
+            "frac": issue, "traffic": None, "peak_source": "ncu smsp__issue_active (%s)" % ncu.get("source", "none committed"),
+            "alu_pipe_utilisation_under_ncu": (ncu.get("alu_pipe_pct") or 0) / 100.0 or None,
+        }
+    dram = ncu.get("dram_bytes_per_perm")
+    roofline.update({
         "perms_per_launch": perms_n, "ms_per_launch": k_ms,
         "list_ms_per_launch": list_ms / calls, "probe_ms_per_launch": probe_ms / calls,
-        "scan_ms_per_launch": scan_ms / calls,
-        "row_kernels_achieved_whole_table": combined,
-        "row_kernels_frac_whole_table": combined / peak if combined else None,
+        "prep_and_scan_ms_per_launch": scan_ms / calls,
         "row_kernels_serialised_ms_per_launch": row_ms / calls,
         "step_ms_with_kernels_overlapped": ms_per_step,
-        "streamed_bytes_per_row_pass": hp.streamed_bytes_per_pass,
         "list_rows": hp.n_rows, "bitmap_rows": hp.n_long, "long_threshold": hp.long_threshold,
-        "note": "algorithmic bytes = one pass over the canonical int32 gene-major CSR per permutation "
-                "(SURVEY.md 8d), apportioned to the genes each row kernel serves; the kernels stream "
-                "2-byte folded indices once per %d permutations and bitmaps once per 64, so frac can "
-                "exceed 1 -- see traffic and DESIGN.md" % hp.perms_per_cta,
-    }
+        # SURVEY.md section 8d's bookkeeping, kept beside the physical bound: one pass over the canonical int32
+        # gene-major CSR per permutation.  The kernels never move those bytes (2-byte folded indices once per %d
+        # permutations, bitmaps shared by 1,024 W genes), so this fraction is an EFFECTIVE one and exceeds 1.
+        "hbm": {"peak": peak, "peak_source": peak_src, "unit": "GB/s",
+                "algorithmic_bytes_per_perm": k_bytes, "algorithmic_bytes_per_perm_whole_table": a_perm,
+                "achieved_algorithmic": hbm_achieved, "effective_frac": hbm_achieved / peak if hbm_achieved else None,
+                "row_kernels_effective_frac_whole_table": combined / peak if combined else None,
+                "traffic": dram * perms_n if dram else None,
+                "dram_frac": dram * perms_n / (k_ms / 1e3) / 1e9 / peak if dram and k_ms > 0 else None,
+                "streamed_bytes_per_row_pass": hp.streamed_bytes_per_pass},
+    })
     cpu = None
-    if world == 1 and not args.no_cpu_baseline:
+    if (world == 1 or args.cpu_check) and not args.no_cpu_baseline:
         from oracle import build as oracle_build, cport
         oracle_build.build()
         threads = os.cpu_count() or 1
@@ -531,7 +618,9 @@ def run_b200(args, rank, world, local_rank):
         cpu = {"value": sample_perms.shape[0] / dt, "unit": UNIT, "cores": threads, "kind": "port",
                "sample": "%d permutations of the same table (of %d), oracle C port of "
                          "pangenome_analysis.py:81-90, %d threads" % (sample_perms.shape[0], perms_n, threads),
-               "single_thread_s_per_perm": t1}
+               "single_thread_s_per_perm": t1,
+               "reference_python": python_reference_sample(coo, eng, n_iter=1 if n >= 2000 else 20)
+               if coo.shape[0] * coo.shape[1] <= 4e9 else {"skipped": "one permutation of this table takes the Python reference about 10 minutes"}}
     config = workload_config(args.workload, coo, perms_total, world, args.scaling)
     if flush is None:
         config["l2_policy"] = "inputs larger than L2: %.0f MB of permutations + %.0f MB of curves + %.0f MB of folded rows per step" % (

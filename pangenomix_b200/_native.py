@@ -22,7 +22,7 @@ EXPORTS = (
     "pgx_plan_bank_order", "pgx_plan_build_bitmap", "pgx_plan_coo_to_csr", "pgx_plan_folded_lists",
     "pgx_plan_missing_genome", "pgx_plan_all_equal_u64", "pgx_plan_balance_rows", "pgx_inflate_raw",
     "pgx_expand_deltas", "pgx_host_plan_create", "pgx_host_plan_destroy", "pgx_plan_create", "pgx_plan_upload",
-    "pgx_plan_destroy",
+    "pgx_plan_destroy", "pgx_set_trace",
 )
 
 
@@ -120,6 +120,8 @@ def load():
     lib.pgx_pan_core_curves_f64.argtypes = [plan_p, vp, i64, vp, vp, vp]
     lib.pgx_pan_core_curves_host.restype = ctypes.c_int
     lib.pgx_pan_core_curves_host.argtypes = [plan_p, vp, i64, vp, i32, i64]
+    lib.pgx_set_trace.restype = ctypes.c_int
+    lib.pgx_set_trace.argtypes = [vp, i64]
     lib.pgx_set_tuning.restype = ctypes.c_int
     lib.pgx_set_tuning.argtypes = [i32, i32, i32]
     lib.pgx_launch_count.restype = i64

@@ -85,7 +85,35 @@ struct Work {
     long long hist_stride;
     uint16_t *ranks;
     long long rank_stride;
+    unsigned long long *trace = nullptr;      // optional CTA timeline (pgx_set_trace), null in normal operation
+    long long trace_capacity = 0;
 };
+
+// CTA timeline for the evidence of how the two row kernels share the SMs (scripts/overlap_trace.py): every CTA of the
+// list kernel (kind 1) and of the probe kernel (kind 2) appends {kind | smid << 8, start, end} in %globaltimer
+// nanoseconds.  trace[0] counts the records.
+unsigned long long *g_trace = nullptr;
+long long g_trace_capacity = 0;
+
+__device__ __forceinline__ unsigned long long global_timer()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ void trace_cta(const Work &work, unsigned kind, unsigned long long t_start)
+{
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    const unsigned long long slot = atomicAdd(work.trace, 1ull);
+    if (static_cast<long long>(slot) < work.trace_capacity) {
+        unsigned long long *rec = work.trace + 1 + 3 * slot;
+        rec[0] = kind | (static_cast<unsigned long long>(smid) << 8);
+        rec[1] = t_start;
+        rec[2] = global_timer();
+    }
+}
 
 // bin ``idx`` (0 .. 2N-1: pan bins then core bins) of a histogram row += v
 template <bool P16>
@@ -103,48 +131,79 @@ __device__ __forceinline__ void hist_add(uint32_t *row, int idx, uint32_t v)
 // first absence 1 if c comes first, 0 otherwise; a gene missing from a single genome c the mirror image.
 // int32 bins hold the core side as "genes lost so far" (bin 0 = G - colsum[first]); packed bins hold the
 // curve's steps (bin 0 = core[0] = colsum[first]), because G - colsum may not fit 16 bits.
-template <bool P16>
+template <bool P16, bool VEC>
 __global__ void __launch_bounds__(256)
 prep_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const Work work, int *__restrict__ bad_rows)
 {
-    extern __shared__ __align__(16) uint16_t s_rank[];   // [N]
+    extern __shared__ __align__(16) uint16_t s_rank[];   // [N] (VEC: N % 8 == 0 and every row 16-byte aligned)
     const int n = plan.n_genomes;
     const long long p = blockIdx.x;
     const uint16_t *__restrict__ perm = perms + p * n;
     const int tid = threadIdx.x;
-
-    for (int g = tid; g < n; g += blockDim.x) s_rank[g] = 0xffffu;
-    __syncthreads();
-    for (int k = tid; k < n; k += blockDim.x) {
-        const uint32_t g = __ldg(perm + k);
-        if (g < static_cast<uint32_t>(n)) s_rank[g] = static_cast<uint16_t>(k);
-    }
-    __syncthreads();
+    const uint32_t last = static_cast<uint32_t>(n - 1);
     uint16_t *__restrict__ ranks = work.ranks + p * work.rank_stride;
     bool missing = false;
-    for (int g = tid; g < n; g += blockDim.x) {
-        const uint16_t r = s_rank[g];
-        missing |= r == 0xffffu;
-        ranks[g] = r;
+
+    // ---- rank row: scatter through shared memory, write out coalesced ----
+    if constexpr (VEC) {
+        for (int g = tid * 8; g < n; g += blockDim.x * 8) *reinterpret_cast<uint4 *>(s_rank + g) = make_uint4(~0u, ~0u, ~0u, ~0u);
+        __syncthreads();
+        for (int k = tid * 8; k < n; k += blockDim.x * 8) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(perm + k));
+            const uint32_t g[8] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (g[j] <= last) s_rank[g[j]] = static_cast<uint16_t>(k + j);
+        }
+        __syncthreads();
+        for (int g = tid * 8; g < n; g += blockDim.x * 8) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(s_rank + g);
+            // a 0xffff left in the row: a genome without a rank
+            missing |= ((v.x & 0xffffu) == 0xffffu) | ((v.x >> 16) == 0xffffu) | ((v.y & 0xffffu) == 0xffffu) | ((v.y >> 16) == 0xffffu) |
+                       ((v.z & 0xffffu) == 0xffffu) | ((v.z >> 16) == 0xffffu) | ((v.w & 0xffffu) == 0xffffu) | ((v.w >> 16) == 0xffffu);
+            *reinterpret_cast<uint4 *>(ranks + g) = v;
+        }
+    } else {
+        for (int g = tid; g < n; g += blockDim.x) s_rank[g] = 0xffffu;
+        __syncthreads();
+        for (int k = tid; k < n; k += blockDim.x) {
+            const uint32_t g = __ldg(perm + k);
+            if (g <= last) s_rank[g] = static_cast<uint16_t>(k);
+        }
+        __syncthreads();
+        for (int g = tid; g < n; g += blockDim.x) {
+            const uint16_t r = s_rank[g];
+            missing |= r == 0xffffu;
+            ranks[g] = r;
+        }
     }
     // a row that is not a permutation of 0 .. N-1 leaves a genome without a rank
     if (missing && bad_rows) atomicAdd(bad_rows, 1);
 
-    // The closed forms: every bin costs a load of perm[k] and a dependent gather from a weight vector.  The loads go
-    // through the read-only path (they cannot alias the stores) and eight bins are in flight per thread.
-    const uint32_t last = static_cast<uint32_t>(n - 1);
+    // ---- closed forms: every bin costs a load of perm[k] and a dependent gather from a weight vector.  The loads go
+    // through the read-only path (they cannot alias the stores) and eight bins are in flight per thread. ----
     const uint32_t first = min(static_cast<uint32_t>(__ldg(perm)), last);
     const int col_first = __ldg(plan.d_colsum + first);
     const uint32_t head_pan = __ldg(plan.d_w_absent + first), head_core = __ldg(plan.d_w_present + first);
     uint32_t *__restrict__ hist = work.hist + p * work.hist_stride;
     constexpr int BINS = 8;
+#pragma unroll 2
     for (int i0 = tid * BINS; i0 < 2 * n; i0 += blockDim.x * BINS) {
         uint32_t g[BINS], v[BINS];
+        if constexpr (VEC) {
+            // N % 8 == 0: the eight bins lie on one side, ranks k0 .. k0 + 7
+            const int k0 = i0 >= n ? i0 - n : i0;
+            const uint4 q = __ldg(reinterpret_cast<const uint4 *>(perm + k0));
+            g[0] = q.x & 0xffffu; g[1] = q.x >> 16; g[2] = q.y & 0xffffu; g[3] = q.y >> 16;
+            g[4] = q.z & 0xffffu; g[5] = q.z >> 16; g[6] = q.w & 0xffffu; g[7] = q.w >> 16;
 #pragma unroll
-        for (int j = 0; j < BINS; ++j) {
-            const int idx = min(i0 + j, 2 * n - 1);
-            const int k = idx >= n ? idx - n : idx;
-            g[j] = min(static_cast<uint32_t>(__ldg(perm + k)), last);
+            for (int j = 0; j < BINS; ++j) g[j] = min(g[j], last);
+        } else {
+#pragma unroll
+            for (int j = 0; j < BINS; ++j) {
+                const int idx = min(i0 + j, 2 * n - 1);
+                g[j] = min(static_cast<uint32_t>(__ldg(perm + (idx >= n ? idx - n : idx))), last);
+            }
         }
 #pragma unroll
         for (int j = 0; j < BINS; ++j) {
@@ -160,14 +219,23 @@ prep_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const Work 
             else if (k == 1) v[j] += side == 0 ? head_pan : head_core;
         }
         if constexpr (P16) {
-            // 8 bins = 4 words, 16 bytes (the rows are 4-byte aligned only: word stores)
+            if constexpr (VEC) {
+                *reinterpret_cast<uint4 *>(hist + (i0 >> 1)) =
+                    make_uint4(v[0] | (v[1] << 16), v[2] | (v[3] << 16), v[4] | (v[5] << 16), v[6] | (v[7] << 16));
+            } else {
 #pragma unroll
-            for (int j = 0; j < BINS; j += 2)
-                if (i0 + j < 2 * n) hist[(i0 + j) >> 1] = v[j] | (i0 + j + 1 < 2 * n ? v[j + 1] << 16 : 0u);
+                for (int j = 0; j < BINS; j += 2)
+                    if (i0 + j < 2 * n) hist[(i0 + j) >> 1] = v[j] | (i0 + j + 1 < 2 * n ? v[j + 1] << 16 : 0u);
+            }
         } else {
+            if constexpr (VEC) {
+                *reinterpret_cast<uint4 *>(hist + i0) = make_uint4(v[0], v[1], v[2], v[3]);
+                *reinterpret_cast<uint4 *>(hist + i0 + 4) = make_uint4(v[4], v[5], v[6], v[7]);
+            } else {
 #pragma unroll
-            for (int j = 0; j < BINS; ++j)
-                if (i0 + j < 2 * n) hist[i0 + j] = v[j];
+                for (int j = 0; j < BINS; ++j)
+                    if (i0 + j < 2 * n) hist[i0 + j] = v[j];
+            }
         }
     }
 }
@@ -260,6 +328,7 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
                       (tid >> 5) * EVENT_QUEUE;
     const uint4 *__restrict__ chunks = reinterpret_cast<const uint4 *>(plan.d_chunks);
     const int4 *__restrict__ tasks = reinterpret_cast<const int4 *>(plan.d_tasks);
+    const unsigned long long t_start = work.trace ? global_timer() : 0ull;
 
     // Persistent CTAs: item = (batch of B permutations, share ``split`` of the tasks).  The whole
     // grid is resident at once, so CTAs of the probe kernel can fill the rest of every SM.
@@ -407,6 +476,7 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
     if (lane < queued) resolve(queue[lane]);
     __syncthreads();                                      // every warp is done with this table
     }
+    if (work.trace && tid == 0) trace_cta(work, 1u, t_start);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -467,6 +537,13 @@ probe_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long
     const int lane = threadIdx.x & 31;
     const long long unit = static_cast<long long>(blockIdx.x) * SLICE_WARPS + (threadIdx.x >> 5);
     if (unit >= n_perm * plan.n_superblocks) return;           // whole warps leave together
+    const unsigned long long t_start = work.trace ? global_timer() : 0ull;
+    struct TraceOnExit {                                       // one record per warp (unit), whichever way the walk ends
+        const Work &work;
+        unsigned long long t_start;
+        int lane;
+        __device__ ~TraceOnExit() { if (work.trace && lane == 0) trace_cta(work, 2u, t_start); }
+    } trace_on_exit{work, t_start, static_cast<int>(threadIdx.x & 31)};
     const long long sb = unit / n_perm, q = unit - sb * n_perm;   // costly superblocks first
 
     const uint32_t *__restrict__ lines = plan.d_bits + (static_cast<size_t>(sb) * n) * (32 * W) + lane * W;
@@ -869,21 +946,28 @@ int aux_for_device(Aux **out)
 
 // prep + the two row kernels of n_perm permutations into ``work`` (histogram rows complete when the stream is)
 template <bool P16>
-int run_rows(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, const Work &work, int *d_bad_rows,
+int run_rows(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, const Work &work_in, int *d_bad_rows,
              cudaStream_t stream, Aux *own_aux, ProfileEvents *ev)
 {
+    Work work = work_in;
+    work.trace = g_trace;
+    work.trace_capacity = g_trace_capacity;
     DeviceLimits lim;
     if (int rc = device_limits(&lim)) return rc;
     const int n = plan->n_genomes;
     const size_t prep_smem = static_cast<size_t>(n) * sizeof(uint16_t);
+    // 16-byte accesses: N % 8 == 0 makes every permutation row aligned; the rank and histogram rows must be too
+    const bool vec = n % 8 == 0 && work.hist_stride % 4 == 0 && work.rank_stride % 8 == 0 &&
+                     ((reinterpret_cast<uintptr_t>(d_perms) | reinterpret_cast<uintptr_t>(work.hist) | reinterpret_cast<uintptr_t>(work.ranks)) & 15) == 0;
+    auto prep = vec ? prep_kernel<P16, true> : prep_kernel<P16, false>;
     if (prep_smem > 48 * 1024)
-        PGX_CUDA(cudaFuncSetAttribute(prep_kernel<P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prep_smem)));
+        PGX_CUDA(cudaFuncSetAttribute(prep, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prep_smem)));
     for (long long p0 = 0; p0 < n_perm; p0 += 2147483647ll) {
         const long long np = min(2147483647ll, n_perm - p0);
         Work w = work;
         w.hist += p0 * work.hist_stride;
         w.ranks += p0 * work.rank_stride;
-        prep_kernel<P16><<<static_cast<unsigned>(np), 256, prep_smem, stream>>>(*plan, d_perms + p0 * n, w, d_bad_rows);
+        prep<<<static_cast<unsigned>(np), 256, prep_smem, stream>>>(*plan, d_perms + p0 * n, w, d_bad_rows);
         PGX_LAUNCH_CHECK("prep_kernel");
     }
     if (ev) PGX_CUDA(cudaEventRecord(ev->prep_done, stream));
@@ -1083,24 +1167,45 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
     const long long n = plan->n_genomes;
     const bool rng = h_perms == nullptr;
     const bool packed = packed_bins(plan);
-    long long block = perms_per_block;
-    if (block <= 0) {
-        // about 32 MB of packed rows per block: large enough for the list kernel's persistent CTAs to amortise their
-        // rank tables, small enough that the first upload and the last download, which nothing overlaps, stay short;
-        // the RNG-fed call is bound by the serial shuffle stream and takes smaller blocks so that its last one is short
-        block = rng ? std::max(32ll, std::min(4096ll, (8ll << 20) / (4 * n))) : std::max(64ll, std::min(1ll << 16, (32ll << 20) / (4 * n)));
-        block = (block + 7) / 8 * 8;
+    // Block schedule.  Large blocks rarefy fastest (the persistent list CTAs amortise their rank tables, the probe
+    // kernel's tail is paid once), but nothing overlaps the first block's upload or the last block's download and
+    // rebuild: the first block is short, the next ones take a quarter of what is left (at most 4 x the base size),
+    // the last ones shrink to half the base size.  The RNG-fed call is bound by the serial shuffle stream: uniform
+    // short blocks, halving at the end so that little is left to do when the last shuffle is drawn.
+    std::vector<long long> first_perm;          // block k covers [first_perm[k], first_perm[k + 1])
+    long long max_block = 0;
+    {
+        long long base = perms_per_block;
+        const bool uniform = base > 0;
+        if (!uniform) {
+            base = rng ? std::max(32ll, std::min(4096ll, (8ll << 20) / (4 * n))) : std::max(64ll, std::min(1ll << 16, (32ll << 20) / (4 * n)));
+            base = (base + 7) / 8 * 8;
+        }
+        long long at = 0;
+        first_perm.push_back(0);
+        while (at < n_perm) {
+            const long long left = n_perm - at;
+            long long take = base;
+            if (!uniform && rng) {
+                if (left < 2 * base) take = std::max(32ll, (left / 2 + 7) / 8 * 8);
+            } else if (!uniform && at > 0) {
+                take = std::min(4 * base, std::max(base / 2, (left / 4 + 7) / 8 * 8));
+            }
+            take = std::min(take, left);
+            at += take;
+            first_perm.push_back(at);
+            max_block = std::max(max_block, take);
+        }
+        // the staging is sized for the largest block of the default schedule even when this call is shorter, so that
+        // the next call need not reallocate
+        if (!uniform) max_block = std::max(max_block, rng ? base : std::min(4 * base, std::max(base, (n_perm / 4 + 7) / 8 * 8)));
     }
     std::lock_guard<std::mutex> lock(g_pipe_mu);
     int dev = 0;
     PGX_CUDA(cudaGetDevice(&dev));
     Pipe &buf = g_pipe;
-    // the staging is sized for the default block even when this call is shorter: the next call need not reallocate
-    if (int rc = acquire(buf, dev, perms_per_block > 0 ? std::min<long long>(block, std::max<long long>(n_perm, 8)) : block,
-                         n, packed, out_f64, rng))
-        return rc;
-    block = std::min<long long>(block, std::max<long long>(n_perm, 8));
-    const long long n_blocks = (n_perm + block - 1) / block;
+    if (int rc = acquire(buf, dev, max_block, n, packed, out_f64, rng)) return rc;
+    const long long n_blocks = static_cast<long long>(first_perm.size()) - 1;
     *buf.bad_rows = 0;
     int *d_bad_rows = nullptr;
     PGX_CUDA(cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_bad_rows), buf.bad_rows, 0));
@@ -1127,7 +1232,7 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
     for (auto &c : parts_done) c.store(0, std::memory_order_relaxed);
     int movers = std::max(1, std::min(rng ? 4 : 12, static_cast<int>(std::thread::hardware_concurrency()) - (rng ? 3 : 2)));
     if (const char *env = getenv("PGX_COPY_THREADS")) movers = std::max(1, std::min(32, atoi(env)));
-    movers = static_cast<int>(std::max<long long>(1, std::min<long long>(movers, block * n / 32768)));
+    movers = static_cast<int>(std::max<long long>(1, std::min<long long>(movers, max_block * n / 32768)));
     const size_t out_elem = out_f64 ? sizeof(double) : sizeof(int32_t);
     auto mover = [&](int t) {
         cudaSetDevice(dev);
@@ -1141,7 +1246,7 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
                 failed.store(1);
                 return;
             }
-            const long long p0 = k * block, cnt = std::min<long long>(block, n_perm - p0);
+            const long long p0 = first_perm[k], cnt = first_perm[k + 1] - p0;
             const long long r0 = cnt * t / movers, r1 = cnt * (t + 1) / movers;
             char *dst = static_cast<char *>(h_curves) + out_elem * 2 * n * p0;
             if (packed) {
@@ -1167,7 +1272,7 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
         }
         if (failed.load(std::memory_order_relaxed)) break;
         Slot &s = buf.slot[k % SLOTS];
-        const long long p0 = k * block, cnt = std::min<long long>(block, n_perm - p0);
+        const long long p0 = first_perm[k], cnt = first_perm[k + 1] - p0;
         const double t_wait = since();
         const uint16_t *src = h_perms ? h_perms + p0 * n : s.h_perm;
         if (rng) rc = pgx_legacy_shuffles(mt_key, mt_pos, n, cnt, s.h_perm);
@@ -1280,6 +1385,13 @@ int pgx_profile_read(double *list_ms, double *probe_ms, double *scan_ms, int64_t
     if (scan_ms) *scan_ms = c;
     if (calls) *calls = static_cast<int64_t>(pgx::g_profile_events.size());
     pgx::g_profile_events.clear();
+    return PGX_OK;
+}
+
+int pgx_set_trace(void *d_trace, int64_t capacity_records)
+{
+    pgx::g_trace = static_cast<unsigned long long *>(d_trace);
+    pgx::g_trace_capacity = d_trace ? capacity_records : 0;
     return PGX_OK;
 }
 

@@ -540,3 +540,42 @@ def test_bernoulli_full_fit_matches_reference(engine_mod, capsys):
     ref_p, got_p = g["fit_x"][:300], res.x[:300]
     margin = np.abs(ref_p - 0.99) > 1e-3
     assert np.array_equal((got_p >= 0.99)[margin], (ref_p >= 0.99)[margin])
+
+
+def test_bernoulli_full_fit_at_c3_size_matches_live_reference(engine_mod, capsys):
+    """Config C3 at its candidate-core size (4,000 genes x 400 genomes, prob_bounds (0.8, 0.99999999)): the whole
+    compute_bernoulli_grid_core_genome call against the fixture the LIVE reference produced (make_golden.py --big):
+    likelihood and gradient at the reference's start point and optimum to 1e-9, the optimum itself, and the
+    core-gene call set {i : p_i >= 0.99} -- identical, with no margin carved out (the distance of the closest p_i to
+    the threshold is printed)."""
+    import hashlib
+    import warnings
+    from pangenomix_b200 import pangenome_analysis as pa, synth
+    g = load_golden("bernoulli_c3_4000x400")
+    x, _, _ = synth.bernoulli_grid_matrix(4000, 400, seed=3)
+    assert hashlib.sha256(x.astype(np.uint8).tobytes()).hexdigest() == str(g["x_digest"])
+    grid = engine_mod.BernoulliGrid(x)
+    for tag, pq in (("init", g["fit_initial"][1:]), ("opt", g["fit_optimum"][1:])):
+        ll, grad = grid.ll_grad(pq)
+        np.testing.assert_allclose(ll, g["ll_" + tag], rtol=LL_RTOL)
+        np.testing.assert_allclose(grad, g["grad_" + tag], rtol=LL_RTOL, atol=1e-9 * np.abs(g["grad_" + tag]).max())
+    index, columns = synth.labels_for(*x.shape)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        df_opt, res = pa.compute_bernoulli_grid_core_genome(pd.DataFrame(x, index=index, columns=columns))
+    capsys.readouterr()
+    assert list(df_opt.index) == ["Loglikelihood"] + ["p_" + s for s in index] + ["q_" + s for s in columns]
+    np.testing.assert_allclose(df_opt["initial"].values, g["fit_initial"], rtol=LL_RTOL)
+    np.testing.assert_allclose(-res.fun, -float(g["fit_fun"]), rtol=LL_RTOL)
+    np.testing.assert_allclose(df_opt["optimum"].values[0], g["fit_optimum"][0], rtol=LL_RTOL)
+    ref_p, got_p = g["fit_x"][:4000], res.x[:4000]
+    tau = 0.99
+    closest = float(np.min(np.abs(ref_p - tau)))
+    worst = float(np.max(np.abs(res.x - g["fit_x"])))
+    with capsys.disabled():
+        print("\n[C3 4,000 x 400] L-BFGS-B iterations %d (reference %d), evaluations %d (reference %d), max |x - x_ref| = %.3g, "
+              "core genes at p >= %.2f: %d (reference %d), closest reference p_i to the threshold: %.3g" % (
+                  res.nit, int(g["fit_nit"]), res.nfev, int(g["fit_nfev"]), worst, tau, int((got_p >= tau).sum()),
+                  int((ref_p >= tau).sum()), closest))
+    assert np.array_equal(got_p >= tau, ref_p >= tau)
+    assert worst < 1e-6
