@@ -469,7 +469,7 @@ def run_b200(args, rank, world, local_rank):
         from pangenomix_b200 import pangenome_analysis as pa, sparse_utils as su
         index, columns = synth.labels_for(n_genes, n)
         lsdf = su.LightSparseDataFrame(index, columns, coo)
-        pa._ENGINE_CACHE[lsdf] = (lsdf.data, eng)              # "uploaded once": reuse the resident table
+        pa._ENGINE_CACHE[lsdf] = (lsdf.data, eng, pa._fingerprint(lsdf.data))              # "uploaded once": reuse the resident table
         iters = int(min(perms_n, 2000))
         np.random.seed(12345)
         with contextlib.redirect_stdout(io.StringIO()):

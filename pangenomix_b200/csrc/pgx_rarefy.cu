@@ -52,6 +52,8 @@
 #include <thread>
 #include <vector>
 
+#include <type_traits>
+
 #include "pgx_common.cuh"
 
 namespace pgx {
@@ -237,6 +239,113 @@ prep_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const Work 
                     if (i0 + j < 2 * n) hist[i0 + j] = v[j];
             }
         }
+    }
+}
+
+// The same work for tables whose rank row and histogram row fit shared memory together (6N bytes with packed bins:
+// N <= 18,000).  The gathers w[perm[k]] of prep_kernel miss L1 once eight CTAs of rank rows share an SM and then cost
+// an L2 sector each (2e8 per 10,000 permutations of C4: the kernel ran at L2 bandwidth, 0.84 ms); here they are turned
+// around: the weight vectors are read in genome order, coalesced, and SCATTERED by rank into a shared-memory image of
+// the histogram row, which then leaves with 16-byte stores.
+template <bool P16>
+__global__ void __launch_bounds__(512)
+prep_scatter_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const Work work, int *__restrict__ bad_rows)
+{
+    using BinT = typename std::conditional<P16, uint16_t, uint32_t>::type;
+    extern __shared__ __align__(16) unsigned char s_raw[];
+    const int n = plan.n_genomes;
+    BinT *s_bins = reinterpret_cast<BinT *>(s_raw);                                   // [2N]: pan bins | core bins
+    uint16_t *s_rank = reinterpret_cast<uint16_t *>(s_raw + ((sizeof(BinT) * 2 * n + 15) & ~size_t(15)));   // [N]
+    const long long p = blockIdx.x;
+    const uint16_t *__restrict__ perm = perms + p * n;
+    const int tid = threadIdx.x;
+    const uint32_t last = static_cast<uint32_t>(n - 1);
+
+    // (every loop below handles eight genomes / ranks per thread with 16-byte accesses when N % 8 == 0)
+    const bool vec = (n & 7) == 0 && (reinterpret_cast<uintptr_t>(perm) & 15) == 0 && (work.rank_stride & 7) == 0 &&
+                     (reinterpret_cast<uintptr_t>(work.ranks) & 15) == 0 &&
+                     ((reinterpret_cast<uintptr_t>(plan.d_w_present) | reinterpret_cast<uintptr_t>(plan.d_w_absent)) & 15) == 0;
+    {
+        uint4 *z = reinterpret_cast<uint4 *>(s_raw);
+        const int bins16 = static_cast<int>((sizeof(BinT) * 2 * n + 15) >> 4), rank16 = (2 * n + 15) >> 4;   // smem is padded to 16 bytes
+        for (int i = tid; i < bins16; i += blockDim.x) z[i] = make_uint4(0u, 0u, 0u, 0u);
+        uint4 *f = reinterpret_cast<uint4 *>(s_rank);
+        for (int i = tid; i < rank16; i += blockDim.x) f[i] = make_uint4(~0u, ~0u, ~0u, ~0u);
+    }
+    __syncthreads();
+    if (vec) {
+        for (int k = tid * 8; k < n; k += blockDim.x * 8) {
+            const uint4 v = __ldg(reinterpret_cast<const uint4 *>(perm + k));
+            const uint32_t g[8] = {v.x & 0xffffu, v.x >> 16, v.y & 0xffffu, v.y >> 16, v.z & 0xffffu, v.z >> 16, v.w & 0xffffu, v.w >> 16};
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+                if (g[j] <= last) s_rank[g[j]] = static_cast<uint16_t>(k + j);
+        }
+    } else {
+        for (int k = tid; k < n; k += blockDim.x) {
+            const uint32_t g = __ldg(perm + k);
+            if (g <= last) s_rank[g] = static_cast<uint16_t>(k);
+        }
+    }
+    __syncthreads();
+    uint16_t *__restrict__ ranks = work.ranks + p * work.rank_stride;
+    bool missing = false;
+    if (vec) {
+        for (int g0 = tid * 8; g0 < n; g0 += blockDim.x * 8) {
+            const uint4 rv = *reinterpret_cast<const uint4 *>(s_rank + g0);
+            *reinterpret_cast<uint4 *>(ranks + g0) = rv;
+            const int4 pa = __ldg(reinterpret_cast<const int4 *>(plan.d_w_present + g0));
+            const int4 pb = __ldg(reinterpret_cast<const int4 *>(plan.d_w_present + g0 + 4));
+            const int4 aa = __ldg(reinterpret_cast<const int4 *>(plan.d_w_absent + g0));
+            const int4 ab = __ldg(reinterpret_cast<const int4 *>(plan.d_w_absent + g0 + 4));
+            const uint32_t r[8] = {rv.x & 0xffffu, rv.x >> 16, rv.y & 0xffffu, rv.y >> 16, rv.z & 0xffffu, rv.z >> 16, rv.w & 0xffffu, rv.w >> 16};
+            const int wp[8] = {pa.x, pa.y, pa.z, pa.w, pb.x, pb.y, pb.z, pb.w};
+            const int wa[8] = {aa.x, aa.y, aa.z, aa.w, ab.x, ab.y, ab.z, ab.w};
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                if (r[j] <= last) {
+                    s_bins[r[j]] = static_cast<BinT>(wp[j]);
+                    s_bins[n + r[j]] = static_cast<BinT>(wa[j]);
+                } else {
+                    missing = true;
+                }
+            }
+        }
+    } else {
+        for (int g = tid; g < n; g += blockDim.x) {
+            const uint32_t r = s_rank[g];
+            ranks[g] = static_cast<uint16_t>(r);
+            if (r <= last) {
+                // genes living in / missing from genome g alone: first presence / first absence at rank r
+                s_bins[r] = static_cast<BinT>(__ldg(plan.d_w_present + g));
+                s_bins[n + r] = static_cast<BinT>(__ldg(plan.d_w_absent + g));
+            } else {
+                missing = true;                       // a genome without a rank: the row is not a permutation
+            }
+        }
+    }
+    if (missing && bad_rows) atomicAdd(bad_rows, 1);
+    __syncthreads();
+    if (tid == 0) {
+        const uint32_t first = min(static_cast<uint32_t>(__ldg(perm)), last);
+        const int col_first = __ldg(plan.d_colsum + first);
+        // bin 0: genes of the first genome; rank 1 also sees the first genome's single-absence / single-genome genes
+        s_bins[0] = static_cast<BinT>(col_first);
+        s_bins[n] = static_cast<BinT>(P16 ? col_first : plan.n_genes - col_first);
+        if (n > 1) {
+            s_bins[1] += static_cast<BinT>(__ldg(plan.d_w_absent + first));
+            s_bins[n + 1] += static_cast<BinT>(__ldg(plan.d_w_present + first));
+        }
+    }
+    __syncthreads();
+    uint32_t *__restrict__ hist = work.hist + p * work.hist_stride;
+    const int words = P16 ? n : 2 * n;                                                // 32-bit words of the row
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(s_bins);
+    if ((words & 3) == 0 && (reinterpret_cast<uintptr_t>(hist) & 15) == 0) {
+        for (int w = tid * 4; w < words; w += blockDim.x * 4)
+            *reinterpret_cast<uint4 *>(hist + w) = *reinterpret_cast<const uint4 *>(src + w);
+    } else {
+        for (int w = tid; w < words; w += blockDim.x) hist[w] = src[w];
     }
 }
 
@@ -851,7 +960,9 @@ int launch_list(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm,
     int threads = g_tuning.threads;
     if (threads <= 0 && getenv("PGX_LIST_THREADS")) threads = atoi(getenv("PGX_LIST_THREADS"));
     const size_t table_bytes = ((static_cast<size_t>(plan.n_genomes + SENTINELS) * B + 7) & ~size_t(7)) * sizeof(uint16_t);
-    if (threads <= 0) threads = table_bytes > 100 * 1024 ? (variant == 2 ? 768 : 1024) : (table_bytes > 40 * 1024 ? 512 : 256);
+    // 896 rather than 1,024 threads beside a table that fills the SM: the probe kernel's CTAs, which run beside this
+    // kernel, then find registers for three CTAs per SM instead of two (C4: 7.88 vs 8.15 ms per step)
+    if (threads <= 0) threads = table_bytes > 100 * 1024 ? (variant == 2 ? 768 : 896) : (table_bytes > 40 * 1024 ? 512 : 256);
     threads = max(32, min(1024, (threads / 32) * 32));
     const size_t smem = table_bytes + static_cast<size_t>(threads / 32) * EVENT_QUEUE * sizeof(uint32_t);
     auto kernel = variant == 2 ? list_kernel<B, 64, P16> : list_kernel<B, 48, P16>;
@@ -955,20 +1066,37 @@ int run_rows(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, co
     DeviceLimits lim;
     if (int rc = device_limits(&lim)) return rc;
     const int n = plan->n_genomes;
-    const size_t prep_smem = static_cast<size_t>(n) * sizeof(uint16_t);
-    // 16-byte accesses: N % 8 == 0 makes every permutation row aligned; the rank and histogram rows must be too
-    const bool vec = n % 8 == 0 && work.hist_stride % 4 == 0 && work.rank_stride % 8 == 0 &&
-                     ((reinterpret_cast<uintptr_t>(d_perms) | reinterpret_cast<uintptr_t>(work.hist) | reinterpret_cast<uintptr_t>(work.ranks)) & 15) == 0;
-    auto prep = vec ? prep_kernel<P16, true> : prep_kernel<P16, false>;
-    if (prep_smem > 48 * 1024)
-        PGX_CUDA(cudaFuncSetAttribute(prep, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prep_smem)));
-    for (long long p0 = 0; p0 < n_perm; p0 += 2147483647ll) {
-        const long long np = min(2147483647ll, n_perm - p0);
-        Work w = work;
-        w.hist += p0 * work.hist_stride;
-        w.ranks += p0 * work.rank_stride;
-        prep<<<static_cast<unsigned>(np), 256, prep_smem, stream>>>(*plan, d_perms + p0 * n, w, d_bad_rows);
-        PGX_LAUNCH_CHECK("prep_kernel");
+    // prep: the shared-memory image of the histogram row when it fits twice per SM, else the gathering version
+    const size_t bins_bytes = ((P16 ? 4 : 8) * static_cast<size_t>(n) + 15) & ~size_t(15);
+    const size_t scatter_smem = bins_bytes + ((static_cast<size_t>(n) * sizeof(uint16_t) + 15) & ~size_t(15));
+    static const bool no_scatter = getenv("PGX_PREP_GATHER") != nullptr;
+    if (scatter_smem <= 110 * 1024 && !no_scatter) {
+        if (scatter_smem > 48 * 1024)
+            PGX_CUDA(cudaFuncSetAttribute(prep_scatter_kernel<P16>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(scatter_smem)));
+        for (long long p0 = 0; p0 < n_perm; p0 += 2147483647ll) {
+            const long long np = min(2147483647ll, n_perm - p0);
+            Work w = work;
+            w.hist += p0 * work.hist_stride;
+            w.ranks += p0 * work.rank_stride;
+            prep_scatter_kernel<P16><<<static_cast<unsigned>(np), 512, scatter_smem, stream>>>(*plan, d_perms + p0 * n, w, d_bad_rows);
+            PGX_LAUNCH_CHECK("prep_scatter_kernel");
+        }
+    } else {
+        const size_t prep_smem = static_cast<size_t>(n) * sizeof(uint16_t);
+        // 16-byte accesses: N % 8 == 0 makes every permutation row aligned; the rank and histogram rows must be too
+        const bool vec = n % 8 == 0 && work.hist_stride % 4 == 0 && work.rank_stride % 8 == 0 &&
+                         ((reinterpret_cast<uintptr_t>(d_perms) | reinterpret_cast<uintptr_t>(work.hist) | reinterpret_cast<uintptr_t>(work.ranks)) & 15) == 0;
+        auto prep = vec ? prep_kernel<P16, true> : prep_kernel<P16, false>;
+        if (prep_smem > 48 * 1024)
+            PGX_CUDA(cudaFuncSetAttribute(prep, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(prep_smem)));
+        for (long long p0 = 0; p0 < n_perm; p0 += 2147483647ll) {
+            const long long np = min(2147483647ll, n_perm - p0);
+            Work w = work;
+            w.hist += p0 * work.hist_stride;
+            w.ranks += p0 * work.rank_stride;
+            prep<<<static_cast<unsigned>(np), 256, prep_smem, stream>>>(*plan, d_perms + p0 * n, w, d_bad_rows);
+            PGX_LAUNCH_CHECK("prep_kernel");
+        }
     }
     if (ev) PGX_CUDA(cudaEventRecord(ev->prep_done, stream));
     // The two row kernels only add into the histogram, in any order: unless per-kernel timing is
@@ -1167,11 +1295,11 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
     const long long n = plan->n_genomes;
     const bool rng = h_perms == nullptr;
     const bool packed = packed_bins(plan);
-    // Block schedule.  Large blocks rarefy fastest (the persistent list CTAs amortise their rank tables, the probe
-    // kernel's tail is paid once), but nothing overlaps the first block's upload or the last block's download and
-    // rebuild: the first block is short, the next ones take a quarter of what is left (at most 4 x the base size),
-    // the last ones shrink to half the base size.  The RNG-fed call is bound by the serial shuffle stream: uniform
-    // short blocks, halving at the end so that little is left to do when the last shuffle is drawn.
+    // Block schedule.  About 32 MB of packed rows per block: large enough for the persistent list CTAs to amortise
+    // their rank tables, small enough that the first upload and the last download + rebuild, which nothing overlaps,
+    // stay short (a schedule with larger middle blocks measured slower: 15.5 vs 14.5 ms per 10,000 permutations of
+    // C4).  The RNG-fed call is bound by the serial shuffle stream: short blocks, halving at the end so that little is
+    // left to do when the last shuffle is drawn.
     std::vector<long long> first_perm;          // block k covers [first_perm[k], first_perm[k + 1])
     long long max_block = 0;
     {
@@ -1188,8 +1316,6 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
             long long take = base;
             if (!uniform && rng) {
                 if (left < 2 * base) take = std::max(32ll, (left / 2 + 7) / 8 * 8);
-            } else if (!uniform && at > 0) {
-                take = std::min(4 * base, std::max(base / 2, (left / 4 + 7) / 8 * 8));
             }
             take = std::min(take, left);
             at += take;
@@ -1198,7 +1324,7 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
         }
         // the staging is sized for the largest block of the default schedule even when this call is shorter, so that
         // the next call need not reallocate
-        if (!uniform) max_block = std::max(max_block, rng ? base : std::min(4 * base, std::max(base, (n_perm / 4 + 7) / 8 * 8)));
+        if (!uniform) max_block = std::max(max_block, base);
     }
     std::lock_guard<std::mutex> lock(g_pipe_mu);
     int dev = 0;
@@ -1230,7 +1356,7 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
     std::atomic<int> failed{0};
     std::vector<std::atomic<int>> parts_done(static_cast<size_t>(n_blocks));
     for (auto &c : parts_done) c.store(0, std::memory_order_relaxed);
-    int movers = std::max(1, std::min(rng ? 4 : 12, static_cast<int>(std::thread::hardware_concurrency()) - (rng ? 3 : 2)));
+    int movers = std::max(1, std::min(rng ? 6 : 12, static_cast<int>(std::thread::hardware_concurrency()) - (rng ? 3 : 2)));
     if (const char *env = getenv("PGX_COPY_THREADS")) movers = std::max(1, std::min(32, atoi(env)));
     movers = static_cast<int>(std::max<long long>(1, std::min<long long>(movers, max_block * n / 32768)));
     const size_t out_elem = out_f64 ? sizeof(double) : sizeof(int32_t);

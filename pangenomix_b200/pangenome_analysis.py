@@ -24,18 +24,35 @@ from .engine import BernoulliGrid, PanCoreEngine
 _ENGINE_CACHE = weakref.WeakKeyDictionary()
 
 
+def _fingerprint(data):
+    """Cheap identity of a COO table: the arrays it is made of (address, length) plus a strided sample of their
+    content (at most 4,096 entries each), so that an in-place edit of ``data.row / .col / .data`` is noticed with
+    high probability without reading the whole table on every call (the reference re-reads it every time,
+    pangenome_analysis.py:74-75).  Tables should still be treated as immutable once they have been rarefied."""
+    parts = [tuple(data.shape), int(getattr(data, "nnz", 0)), getattr(data, "format", None)]
+    for name in ("row", "col", "data", "indices", "indptr"):
+        arr = getattr(data, name, None)
+        if isinstance(arr, np.ndarray):
+            step = max(1, arr.shape[0] // 4096)
+            sample = np.ascontiguousarray(arr[::step])
+            parts.append((name, arr.__array_interface__["data"][0], arr.shape[0], str(arr.dtype), hash(sample.tobytes())))
+    return tuple(parts)
+
+
 def _engine_for(df_genes, device=None):
-    """One uploaded matrix per LSDF object ("uploaded once"); re-planned if .data is replaced."""
+    """One uploaded matrix per LSDF object ("uploaded once"); re-planned if ``.data`` is replaced or (as far as the
+    sampled fingerprint sees) edited in place."""
     try:
         cached = _ENGINE_CACHE.get(df_genes)
     except TypeError:
         cached = None
-    if cached is not None and cached[0] is df_genes.data and \
+    mark = _fingerprint(df_genes.data)
+    if cached is not None and cached[0] is df_genes.data and cached[2] == mark and \
             (device is None or str(cached[1].device) == str(device)):
         return cached[1]
     engine = PanCoreEngine(df_genes.data, device=device)
     try:
-        _ENGINE_CACHE[df_genes] = (df_genes.data, engine)
+        _ENGINE_CACHE[df_genes] = (df_genes.data, engine, mark)
     except TypeError:
         pass
     return engine
