@@ -27,7 +27,8 @@ KEEP = [
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__block_size",
     "launch__grid_size", "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.max",
     "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
-    "smsp__cycles_active.avg",
+    "smsp__cycles_active.avg", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
+    "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
 ]
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
@@ -54,8 +55,12 @@ def main():
                     vals[k] = float(r[idx[k]].replace(",", "")) * SCALE.get(units[idx[k]], 1.0)
                 except ValueError:
                     pass
-            kind = "list" if "list_kernel" in name else ("probe" if "probe_kernel" in name else
-                                                          ("scan" if "scan_kernel" in name else ("prep" if "prep_kernel" in name else short)))
+            kind = short
+            for key, tag_ in (("list_kernel", "list"), ("probe_kernel", "probe"), ("scan_kernel", "scan"), ("prep_scatter_kernel", "prep"),
+                              ("prep_kernel", "prep"), ("grid_kernel", "grid"), ("finish_kernel", "finish"), ("heaps_kernel", "heaps")):
+                if key in name:
+                    kind = tag_
+                    break
             lds = vals.get("smsp__inst_executed_op_shared_ld.sum") or vals.get("sm__sass_inst_executed_op_shared_ld.sum")
             summary[kind] = {
                 "kernel": short, "ms_under_ncu": vals.get("gpu__time_duration.sum"),
@@ -66,6 +71,9 @@ def main():
                 "wavefronts_per_shared_load": (vals.get("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", 0.0) / lds) if lds else None,
                 "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_elapsed"),
                 "alu_pipe_pct": vals.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
+                "fp64_pipe_pct": vals.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
+                or vals.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
+                "active_lanes_per_instruction": vals.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
                 "l2_bytes_per_perm": vals.get("lts__t_bytes.sum", 0.0) / perms,
                 "source": "profiles/%s_%s_ncu_raw_selected.csv (%d permutations per launch)" % (tag, workload, perms),
             }
@@ -75,7 +83,7 @@ def main():
             doc = json.load(f)
     except (OSError, ValueError):
         doc = {}
-    doc[workload] = summary
+    doc.setdefault(workload, {}).update(summary)
     with open(path, "w") as f:
         json.dump(doc, f, indent=1, sort_keys=True)
     details = subprocess.run(["ncu", "-i", rep, "--page", "details"], check=True, capture_output=True, text=True).stdout
