@@ -24,13 +24,16 @@ for _ in range(3):
     eng.curves_device(d_perms, out=out)
 torch.cuda.synchronize()
 ref = out[:64].cpu().numpy()
-capacity = n_perm * max(1, eng.host_plan.n_superblocks) + 4096
+n_steps = int(sys.argv[4]) if len(sys.argv) > 4 else 1          # back-to-back steps; the LAST one is analysed
+capacity = n_steps * (n_perm * max(1, eng.host_plan.n_superblocks) + 4096)
 trace = torch.zeros(1 + 3 * capacity, dtype=torch.int64, device="cuda")
 lib = _native.load()
 _native.check(lib.pgx_set_trace(trace.data_ptr(), capacity))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-e0.record()
-eng.curves_device(d_perms, out=out)
+for i in range(n_steps):
+    if i == n_steps - 1:
+        e0.record()
+    eng.curves_device(d_perms, out=out)
 e1.record()
 torch.cuda.synchronize()
 _native.check(lib.pgx_set_trace(None, 0))
@@ -38,6 +41,16 @@ assert np.array_equal(out[:64].cpu().numpy(), ref)
 t = trace.cpu().numpy()
 count = int(t[0])
 rec = t[1:1 + 3 * min(count, capacity)].reshape(-1, 3)
+if n_steps > 1:
+    # the list kernel leaves exactly one record per CTA and step: the last step starts with the last 148-CTA batch
+    lst_all = np.flatnonzero((rec[:, 0] & 0xff) == 1)
+    per_step = lst_all.size // n_steps
+    last_start = rec[lst_all[np.argsort(rec[lst_all, 1])][-per_step:], 1].min()
+    prev_end = np.sort(rec[lst_all, 2])[-per_step - 1] if lst_all.size > per_step else 0
+    keep = rec[:, 1] > prev_end if prev_end else np.ones(rec.shape[0], dtype=bool)
+    # probe warps of the last step: those that started after the previous step's scan, i.e. after prev_end
+    rec = rec[keep]
+    count = int(rec.shape[0])
 kind, sm = rec[:, 0] & 0xff, rec[:, 0] >> 8
 t0 = int(rec[:, 1].min())
 start, end = (rec[:, 1] - t0) / 1e6, (rec[:, 2] - t0) / 1e6           # ms
@@ -53,6 +66,7 @@ total = (end[prb] - start[prb]).sum()
 per_sm_probe = np.bincount(sm[prb].astype(np.int64), weights=(end[prb] - start[prb]), minlength=int(sm.max()) + 1)
 doc = {
     "workload": name, "perms": n_perm, "records": count, "step_ms_cuda_events": e0.elapsed_time(e1),
+    "back_to_back_steps": n_steps, "analysed": "the last step",
     "list_ctas": int(lst.sum()), "probe_warps": int(prb.sum()),
     "list_kernel_span_ms": list_span, "probe_kernel_span_ms": probe_span,
     "probe_warp_time_inside_list_span_frac": float(inside / total),
