@@ -27,6 +27,13 @@ KEEP = [
     "l1tex__throughput.avg.pct_of_peak_sustained_elapsed", "launch__registers_per_thread", "launch__block_size",
     "launch__grid_size", "launch__shared_mem_per_block_dynamic", "sm__cycles_elapsed.avg", "sm__cycles_elapsed.max",
     "smsp__average_warp_latency_issue_stalled_short_scoreboard.ratio", "smsp__average_warp_latency_issue_stalled_long_scoreboard.ratio",
+    "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg", "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_lgds.avg",
+    "SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_shared.avg", "sm__cycles_elapsed.sum",
+    "smsp__sass_inst_executed_op_shared_ld.sum", "smsp__sass_inst_executed_op_shared_st.sum",
+    "smsp__sass_inst_executed_op_global_ld.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active", "lts__t_sectors.sum",
+    "smsp__average_warps_issue_stalled_short_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_long_scoreboard_per_issue_active.ratio",
+    "smsp__average_warps_issue_stalled_math_pipe_throttle_per_issue_active.ratio",
     "smsp__cycles_active.avg", "sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active",
     "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active", "smsp__thread_inst_executed_per_inst_executed.ratio",
 ]
@@ -61,20 +68,26 @@ def main():
                 if key in name:
                     kind = tag_
                     break
-            lds = vals.get("smsp__inst_executed_op_shared_ld.sum") or vals.get("sm__sass_inst_executed_op_shared_ld.sum")
+            lds = vals.get("smsp__sass_inst_executed_op_shared_ld.sum") or vals.get("smsp__inst_executed_op_shared_ld.sum")
+            sms = (vals.get("sm__cycles_elapsed.sum", 0.0) / vals["sm__cycles_elapsed.avg"]) if vals.get("sm__cycles_elapsed.avg") else 148.0
+            wavefronts = vals.get("l1tex__data_pipe_lsu_wavefronts.sum") or \
+                (vals.get("SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts.avg", 0.0) * sms)
             summary[kind] = {
                 "kernel": short, "ms_under_ncu": vals.get("gpu__time_duration.sum"),
                 "dram_bytes_per_perm": (vals.get("dram__bytes_read.sum", 0.0) + vals.get("dram__bytes_write.sum", 0.0)) / perms,
-                "lsu_wavefronts_per_perm": vals.get("l1tex__data_pipe_lsu_wavefronts.sum", 0.0) / perms or None,
+                "lsu_wavefronts_per_perm": wavefronts / perms or None,
+                "lsu_wavefronts_shared_per_perm": vals.get("SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_shared.avg", 0.0) * sms / perms,
+                "lsu_wavefronts_global_per_perm": vals.get("SM_A.TriageCompute.l1tex__data_pipe_lsu_wavefronts_mem_lgds.avg", 0.0) * sms / perms,
                 "lsu_pipe_pct_of_peak": vals.get("l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed"),
                 "shared_ld_wavefronts_per_perm": vals.get("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", 0.0) / perms,
                 "wavefronts_per_shared_load": (vals.get("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_ld.sum", 0.0) / lds) if lds else None,
-                "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_elapsed"),
+                "issue_active_pct": vals.get("smsp__issue_active.avg.pct_of_peak_sustained_active")
+                or vals.get("smsp__issue_active.avg.pct_of_peak_sustained_elapsed"),
                 "alu_pipe_pct": vals.get("sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active"),
                 "fp64_pipe_pct": vals.get("sm__inst_executed_pipe_fp64.avg.pct_of_peak_sustained_active")
                 or vals.get("sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active"),
                 "active_lanes_per_instruction": vals.get("smsp__thread_inst_executed_per_inst_executed.ratio"),
-                "l2_bytes_per_perm": vals.get("lts__t_bytes.sum", 0.0) / perms,
+                "l2_bytes_per_perm": (vals.get("lts__t_bytes.sum") or 32.0 * vals.get("lts__t_sectors.sum", 0.0)) / perms,
                 "source": "profiles/%s_%s_ncu_raw_selected.csv (%d permutations per launch)" % (tag, workload, perms),
             }
     path = os.path.join(REPO, "profiles", "roofline_traffic.json")

@@ -1,5 +1,5 @@
 #!/bin/bash
-# Host helpers of libpgx_b200 (csrc/pgx_rng.cpp, csrc/pgx_plan.cpp: threaded C++ with hand-managed buffers)
+# Host half of libpgx_b200 (csrc/pgx_rng.cpp, pgx_plan.cpp, pgx_plan_build.cpp, pgx_expand.cpp, pgx_inflate.cpp: threaded C++)
 # under AddressSanitizer + UndefinedBehaviorSanitizer, driven by the CPU test suite.  No GPU needed.
 #
 #   bash scripts/sanitize_host.sh [pytest args]      (default: the plan / ABI / sparse_utils / distributed tests)
@@ -21,12 +21,12 @@ else
   LINK="-Xlinker $(gcc -print-file-name=libubsan.so)"
   PRE="$(gcc -print-file-name=libasan.so) $(gcc -print-file-name=libubsan.so)"
 fi
-for src in pgx_rng pgx_plan pgx_inflate; do
+for src in pgx_rng pgx_plan pgx_inflate pgx_expand pgx_plan_build; do
   g++ -O1 -g -std=c++17 -fPIC -pthread $SAN -I "$REPO/include" -c "$CSRC/$src.cpp" -o "$OUT/$src.o"
 done
 nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -lineinfo -Xcompiler -fPIC,-O3,-pthread -shared \
   -I "$REPO/include" -I "$CSRC" -o "$OUT/libpgx_b200.so" \
-  "$CSRC/pgx_api.cu" "$CSRC/pgx_rarefy.cu" "$CSRC/pgx_bernoulli.cu" "$CSRC/pgx_heaps.cu" "$OUT/pgx_rng.o" "$OUT/pgx_plan.o" "$OUT/pgx_inflate.o" \
+  "$CSRC/pgx_api.cu" "$CSRC/pgx_rarefy.cu" "$CSRC/pgx_bernoulli.cu" "$CSRC/pgx_heaps.cu" "$OUT/pgx_rng.o" "$OUT/pgx_plan.o" "$OUT/pgx_inflate.o" "$OUT/pgx_expand.o" "$OUT/pgx_plan_build.o" \
   $LINK
 cd "$REPO"
 if [ $# -eq 0 ]; then set -- tests/test_plan.py tests/test_abi_cpu.py tests/test_sparse_utils.py tests/test_distributed_cpu.py; fi
