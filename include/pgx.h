@@ -13,6 +13,11 @@
  *   pgx_legacy_shuffles          replaces the np.arange + np.random.shuffle pair at :84-85
  *                                (numpy legacy MT19937 stream, bit-exact)
  *   pgx_heaps_fit                batched counterpart of __fit_heaps_single__ (:39-48)
+ *   pgx_ks_montecarlo[_host]     replaces the simulation loop of ks_montecarlo_bbn (:471-480) incl. the
+ *                                np.random.choice draws of draw_bbn (:484-492), bit-exact
+ *   pgx_coo_marginals[_host],    replace ``gene_mat.sum(axis=1)`` + collections.Counter at :352-355
+ *   pgx_frequency_spectrum       (LightSparseDataFrame.sum, sparse_utils.py:284-292;
+ *                                count_gene_occurence, core_genome.py:127-155)
  *
  * Conventions: every function returns 0 on success and a non-zero code otherwise;
  * pgx_last_error() then returns a thread-local message.  No C++ types, exceptions or
@@ -31,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PGX_VERSION 300
+#define PGX_VERSION 310
 
 enum {
     PGX_OK = 0,
@@ -296,6 +301,52 @@ int pgx_expand_deltas(const uint16_t *h_deltas, int64_t n_rows, int32_t n_genome
  * can np.random.set_state() it.  Requires n <= 65535. */
 int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n, int64_t count,
                         uint16_t *h_perms);
+
+/* Raw 32-bit outputs of the same stream (host): ``count`` words continuing the MT19937 state, written back
+ * advanced.  numpy's legacy random_sample() consumes two of them per double, (a >> 5, b >> 6) -> (a * 2^26 + b) / 2^53;
+ * RandomState.choice(p=...) -- draw_bbn, pangenome_analysis.py:484-492 -- one such double per draw. */
+int pgx_legacy_random_raw(uint32_t *mt_key, int32_t *mt_pos, int64_t count, uint32_t *h_out);
+
+/* Marginals of a COO presence/absence table on the device: d_row_sum[g] = entries of gene g (what
+ * ``gene_mat.sum(axis=1)`` gives for a binary table without duplicates, pangenome_analysis.py:354-355; also
+ * LightSparseDataFrame.sum, sparse_utils.py:284-292, and count_gene_occurence, core_genome.py:127-155),
+ * d_col_sum[c] = entries of genome c.  Entries outside the table are skipped and counted in *d_bad.
+ *   accumulate == 0 : the three outputs are zeroed first;  != 0 : counts are added (tables sent in chunks)
+ * Asynchronous on ``stream``. */
+int pgx_coo_marginals(const int32_t *d_row, const int32_t *d_col, int64_t nnz, int32_t n_genes, int32_t n_genomes,
+                      int32_t *d_row_sum, int32_t *d_col_sum, int32_t *d_bad, int32_t accumulate, void *stream);
+
+/* Gene-frequency spectrum of the row sums: d_spectrum[m] (int64 [N + 1]) = genes present in exactly m genomes,
+ * d_first_gene[m] (int32 [N + 1]) = the lowest gene index among them (INT32_MAX when there is none): the order of
+ * first appearance is the order of the collections.Counter the reference slices at pangenome_analysis.py:355, :364.
+ * Row sums above N (duplicate entries) are counted at N.  Asynchronous on ``stream``. */
+int pgx_frequency_spectrum(const int32_t *d_row_sum, int64_t n_genes, int32_t n_genomes, int64_t *d_spectrum,
+                           int32_t *d_first_gene, void *stream);
+
+/* Both of the above for a table in host memory (row / col as read_lsdf returns them in ``.data``); synchronous.
+ * h_spectrum / h_first_gene may be null.  Entries outside the table make the call fail with PGX_ERR_INVALID. */
+int pgx_coo_marginals_host(const int32_t *h_row, const int32_t *h_col, int64_t nnz, int32_t n_genes, int32_t n_genomes,
+                           int32_t *h_row_sum, int32_t *h_col_sum, int64_t *h_spectrum, int32_t *h_first_gene);
+
+/* Monte-Carlo Kolmogorov-Smirnov statistics of ks_montecarlo_bbn (pangenome_analysis.py:457-482): for iteration i,
+ * n_samples draws of ``np.random.choice(np.arange(sim_limit), p=probs)`` (draw_bbn, :484-492), their eCDF
+ * (ecdf_from_counts, :494-499) and d_ks_sim[i] = max |eCDF - model_cdf| (:479), float64, bit-exact.
+ *   d_raw        : [iterations][n_samples][2] uint32, the raw MT19937 words of the draws in stream order
+ *                  (pgx_legacy_random_raw), 8-byte aligned
+ *   d_choice_cdf : [sim_limit] float64, ``cdf = probs.cumsum(); cdf /= cdf[-1]`` as numpy's choice forms it
+ *   d_model_cdf  : [sim_limit] float64, ``np.cumsum(model_pmf)`` of :464-465
+ *   d_scratch    : pgx_ks_scratch_bytes(iterations, sim_limit) bytes
+ * iterations <= 65,535 per call, n_samples < 2^31.  Deterministic.  Asynchronous on ``stream``. */
+size_t pgx_ks_scratch_bytes(int64_t iterations, int32_t sim_limit);
+int pgx_ks_montecarlo(const uint32_t *d_raw, int64_t iterations, int64_t n_samples, const double *d_choice_cdf,
+                      const double *d_model_cdf, int32_t sim_limit, double *d_ks_sim, void *d_scratch, void *stream);
+
+/* The same with host buffers, drawing from the numpy-legacy MT19937 state (mt_key[624] / mt_pos as
+ * np.random.get_state() reports them; advanced in place by the 2 * iterations * n_samples words the reference's
+ * np.random.choice call consumes).  The generator (host, serial) fills one block of iterations while the previous one
+ * is uploaded and reduced on the current device.  Synchronous; one call at a time per process. */
+int pgx_ks_montecarlo_host(uint32_t *mt_key, int32_t *mt_pos, int64_t iterations, int64_t n_samples,
+                           const double *h_choice_cdf, const double *h_model_cdf, int32_t sim_limit, double *h_ks_sim);
 
 #ifdef __cplusplus
 }

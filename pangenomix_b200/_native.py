@@ -22,7 +22,8 @@ EXPORTS = (
     "pgx_plan_bank_order", "pgx_plan_build_bitmap", "pgx_plan_coo_to_csr", "pgx_plan_folded_lists",
     "pgx_plan_missing_genome", "pgx_plan_all_equal_u64", "pgx_plan_balance_rows", "pgx_inflate_raw",
     "pgx_expand_deltas", "pgx_host_plan_create", "pgx_host_plan_destroy", "pgx_plan_create", "pgx_plan_upload",
-    "pgx_plan_destroy", "pgx_set_trace",
+    "pgx_plan_destroy", "pgx_set_trace", "pgx_legacy_random_raw", "pgx_coo_marginals", "pgx_frequency_spectrum",
+    "pgx_coo_marginals_host", "pgx_ks_scratch_bytes", "pgx_ks_montecarlo", "pgx_ks_montecarlo_host",
 )
 
 
@@ -167,6 +168,20 @@ def load():
     lib.pgx_heaps_fit.argtypes = [vp, i32, i64, i64, i64, vp, vp, vp, vp]
     lib.pgx_legacy_shuffles.restype = ctypes.c_int
     lib.pgx_legacy_shuffles.argtypes = [vp, ctypes.POINTER(i32), i64, i64, vp]
+    lib.pgx_legacy_random_raw.restype = ctypes.c_int
+    lib.pgx_legacy_random_raw.argtypes = [vp, ctypes.POINTER(i32), i64, vp]
+    lib.pgx_coo_marginals.restype = ctypes.c_int
+    lib.pgx_coo_marginals.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, i32, vp]
+    lib.pgx_frequency_spectrum.restype = ctypes.c_int
+    lib.pgx_frequency_spectrum.argtypes = [vp, i64, i32, vp, vp, vp]
+    lib.pgx_coo_marginals_host.restype = ctypes.c_int
+    lib.pgx_coo_marginals_host.argtypes = [vp, vp, i64, i32, i32, vp, vp, vp, vp]
+    lib.pgx_ks_scratch_bytes.restype = ctypes.c_size_t
+    lib.pgx_ks_scratch_bytes.argtypes = [i64, i32]
+    lib.pgx_ks_montecarlo.restype = ctypes.c_int
+    lib.pgx_ks_montecarlo.argtypes = [vp, i64, i64, vp, vp, i32, vp, vp, vp]
+    lib.pgx_ks_montecarlo_host.restype = ctypes.c_int
+    lib.pgx_ks_montecarlo_host.argtypes = [vp, ctypes.POINTER(i32), i64, i64, vp, vp, i32, vp]
     lib.pgx_profile_enable.restype = ctypes.c_int
     lib.pgx_profile_enable.argtypes = [i32]
     lib.pgx_profile_read.restype = ctypes.c_int

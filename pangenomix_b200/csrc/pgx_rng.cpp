@@ -733,3 +733,111 @@ extern "C" int pgx_legacy_shuffles(uint32_t *mt_key, int32_t *mt_pos, int64_t n,
     }
     return PGX_OK;
 }
+
+// Raw 32-bit outputs of the same stream: what numpy's legacy ``random_sample`` (two words per double), and through it
+// ``RandomState.choice(p=...)`` -- draw_bbn, /root/reference/pangenomix/pangenome_analysis.py:484-492 -- consume.
+namespace {
+// Sequential writer into a large destination: whole 64-byte lines leave with streaming stores (no read-for-ownership
+// of the destination), assembled in a pending line so that neither the block boundaries of the generator (624 words)
+// nor the alignment of the destination ever split a line; ordinary stores for the unaligned head and tail.
+struct StreamWriter {
+    uint32_t *dst;
+    alignas(64) uint32_t line[16];
+    int pending = 0;                                    // words waiting in ``line`` (dst is 64-byte aligned while > 0)
+    bool wide;
+    StreamWriter(uint32_t *d, bool avx512) : dst(d), wide(avx512) {}
+#if PGX_X86
+    __attribute__((target("avx512f"))) static void lines512(uint32_t *d, const uint32_t *src, int64_t lines)
+    {
+        for (int64_t i = 0; i < lines; ++i)
+            _mm512_stream_si512(reinterpret_cast<__m512i *>(d + 16 * i), _mm512_loadu_si512(src + 16 * i));
+    }
+    static void lines128(uint32_t *d, const uint32_t *src, int64_t lines)
+    {
+        for (int64_t i = 0; i < 4 * lines; ++i)
+            _mm_stream_si128(reinterpret_cast<__m128i *>(d + 4 * i), _mm_loadu_si128(reinterpret_cast<const __m128i *>(src + 4 * i)));
+    }
+#endif
+    void put_lines(const uint32_t *src, int64_t lines)
+    {
+#if PGX_X86
+        if (wide) lines512(dst, src, lines);
+        else lines128(dst, src, lines);
+#else
+        memcpy(dst, src, sizeof(uint32_t) * 16 * lines);
+#endif
+        dst += 16 * lines;
+    }
+    void push(const uint32_t *src, int64_t n)
+    {
+        while (n > 0 && pending == 0 && (reinterpret_cast<uintptr_t>(dst) & 63)) {    // head of the destination
+            *dst++ = *src++;
+            --n;
+        }
+        if (pending > 0) {
+            const int fill = static_cast<int>(std::min<int64_t>(16 - pending, n));
+            memcpy(line + pending, src, sizeof(uint32_t) * fill);
+            pending += fill;
+            src += fill;
+            n -= fill;
+            if (pending < 16) return;
+            put_lines(line, 1);
+            pending = 0;
+        }
+        const int64_t lines = n / 16;
+        if (lines > 0) {
+            put_lines(src, lines);
+            src += 16 * lines;
+            n -= 16 * lines;
+        }
+        if (n > 0) {
+            memcpy(line, src, sizeof(uint32_t) * n);
+            pending = static_cast<int>(n);
+        }
+    }
+    void finish()
+    {
+        if (pending > 0) memcpy(dst, line, sizeof(uint32_t) * pending);
+#if PGX_X86
+        _mm_sfence();                                   // before the caller hands the buffer to a copy engine
+#endif
+    }
+};
+}  // namespace
+
+extern "C" int pgx_legacy_random_raw(uint32_t *mt_key, int32_t *mt_pos, int64_t count, uint32_t *h_out)
+{
+    if (!mt_key || !mt_pos || (!h_out && count > 0))
+        return pgx::fail(PGX_ERR_INVALID, "null pointer passed to pgx_legacy_random_raw");
+    if (count < 0 || *mt_pos < 0 || *mt_pos > 624) return pgx::fail(PGX_ERR_INVALID, "bad MT19937 position / count");
+    static Mt19937 mt_storage;
+    static std::mutex call_mu;
+    std::lock_guard<std::mutex> call_lock(call_mu);
+    Mt19937 &mt = mt_storage;
+    memcpy(mt.key, mt_key, sizeof(uint32_t) * 624);
+    mt.pos = *mt_pos;
+    mt.carried = false;
+#if PGX_X86
+    mt.avx2 = __builtin_cpu_supports("avx2") && !getenv("PGX_RNG_SCALAR");
+    mt.avx512 = mt.avx2 && __builtin_cpu_supports("avx512f") && !getenv("PGX_RNG_NO_AVX512");
+#else
+    mt.avx2 = false;
+    mt.avx512 = false;
+#endif
+    mt.bmi2 = false;
+    if (mt.pos < 624) mt.temper_scalar();
+    StreamWriter writer(h_out, mt.avx512);
+    int64_t done = 0;
+    while (done < count) {
+        if (mt.pos == 624) mt.refill();                 // numpy refills lazily too: a call that ends on a block
+                                                        // boundary reports position 624 of the old key
+        const int64_t take = std::min<int64_t>(624 - mt.pos, count - done);
+        writer.push(mt.out + mt.pos, take);
+        mt.pos += static_cast<int>(take);
+        done += take;
+    }
+    writer.finish();
+    memcpy(mt_key, mt.key, sizeof(uint32_t) * 624);
+    *mt_pos = mt.pos;
+    return PGX_OK;
+}

@@ -317,3 +317,86 @@ class BernoulliGrid:
 
     def gradient(self, p, q):
         return self.ll_grad(np.concatenate((p, q)))[1]
+
+
+# ---- beta-binomial core estimate (pangenome_analysis.py:295-400): marginals and Monte-Carlo KS ---------------
+def table_marginals(data, device=None, spectrum=True):
+    """Row sums, column sums and the gene-frequency spectrum of a binary COO table, counted on the GPU
+    (pgx_coo_marginals_host): what ``gene_mat.sum(axis=1)`` + collections.Counter give at
+    pangenome_analysis.py:354-355 and LightSparseDataFrame.sum at sparse_utils.py:284-292.
+
+    ``data`` is scipy sparse (``df_genes.data``); every stored value must be 1 and (gene, genome) pairs must not
+    repeat -- the producers' invariant (pangenome.py:631-650) -- since entries are COUNTED, not summed.  Returns
+    (row_sum int64 [G], col_sum int64 [N], spectrum int64 [N + 1], first_gene int32 [N + 1]); the last two are None
+    with ``spectrum=False``.
+    """
+    torch = _torch()
+    dev = _require_cuda(device)
+    coo = data.tocoo()
+    n_genes, n_genomes = (int(v) for v in coo.shape)
+    if n_genes > 2 ** 31 - 1 or n_genomes > 2 ** 31 - 1:
+        raise ValueError("table too large")
+    values = np.asarray(coo.data)
+    if values.dtype in (np.dtype(np.int64), np.dtype(np.float64)) and values.flags.c_contiguous:
+        one = 1 if values.dtype == np.dtype(np.int64) else int(np.float64(1.0).view(np.uint64))
+        all_ones = bool(_native.load().pgx_plan_all_equal_u64(values.ctypes.data, values.shape[0], one, 0))
+    else:
+        all_ones = values.dtype != object and bool(np.all(values == 1))
+    if values.size and not all_ones:
+        raise ValueError("table_marginals counts entries: every stored value must be 1 (binary presence/absence table)")
+    row = np.ascontiguousarray(coo.row, dtype=np.int32)
+    col = np.ascontiguousarray(coo.col, dtype=np.int32)
+    row_sum = np.empty(n_genes, dtype=np.int32)
+    col_sum = np.empty(n_genomes, dtype=np.int32)
+    spec = np.empty(n_genomes + 1, dtype=np.int64) if spectrum else None
+    first = np.empty(n_genomes + 1, dtype=np.int32) if spectrum else None
+    with torch.cuda.device(dev):
+        _native.check(_native.load().pgx_coo_marginals_host(
+            row.ctypes.data, col.ctypes.data, int(row.shape[0]), n_genes, n_genomes, row_sum.ctypes.data,
+            col_sum.ctypes.data, spec.ctypes.data if spectrum else None, first.ctypes.data if spectrum else None))
+    if row_sum.size and int(row_sum.max()) > n_genomes:
+        raise ValueError("duplicate (gene, genome) entries in the table")
+    return row_sum.astype(np.int64), col_sum.astype(np.int64), spec, first
+
+
+def legacy_random_raw(count):
+    """``count`` raw 32-bit words from the GLOBAL legacy numpy stream (advanced exactly), as uint32."""
+    out = np.empty(int(count), dtype=np.uint32)
+    state = np.random.get_state()
+    if state[0] != "MT19937":
+        raise _native.PgxError("the global numpy RNG is not MT19937")
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int32(int(state[2]))
+    _native.check(_native.load().pgx_legacy_random_raw(key.ctypes.data, ctypes.byref(pos), out.shape[0], out.ctypes.data))
+    np.random.set_state((state[0], key, int(pos.value), state[3], state[4]))
+    return out
+
+
+def ks_montecarlo_statistics(choice_cdf, model_cdf, n_samples, iterations, device=None):
+    """ks_sim of pangenome_analysis.py:471-480: ``iterations`` simulated KS statistics of samples of ``n_samples``
+    draws from the choice CDF, drawn from the GLOBAL legacy numpy stream exactly as the reference's
+    ``np.random.choice(Xs, size=n_samples * iterations, p=probs)`` (:492) draws them (pgx_ks_montecarlo_host)."""
+    torch = _torch()
+    dev = _require_cuda(device)
+    choice_cdf = np.ascontiguousarray(choice_cdf, dtype=np.float64)
+    model_cdf = np.ascontiguousarray(model_cdf, dtype=np.float64)
+    if choice_cdf.ndim != 1 or choice_cdf.shape != model_cdf.shape or choice_cdf.shape[0] < 1:
+        raise ValueError("choice_cdf and model_cdf must be 1-D arrays of the same length")
+    iterations, n_samples = int(iterations), int(n_samples)
+    out = np.empty(iterations, dtype=np.float64)
+    state = np.random.get_state()
+    if state[0] != "MT19937":
+        raise _native.PgxError("the global numpy RNG is not MT19937")
+    key = np.ascontiguousarray(state[1], dtype=np.uint32).copy()
+    pos = ctypes.c_int32(int(state[2]))
+    lib = _native.load()
+    with torch.cuda.device(dev):
+        done = 0
+        while done < iterations:                      # the C call takes at most 65,535 iterations
+            cnt = min(65535, iterations - done)
+            _native.check(lib.pgx_ks_montecarlo_host(
+                key.ctypes.data, ctypes.byref(pos), cnt, n_samples, choice_cdf.ctypes.data, model_cdf.ctypes.data,
+                int(choice_cdf.shape[0]), out[done:].ctypes.data))
+            done += cnt
+    np.random.set_state((state[0], key, int(pos.value), state[3], state[4]))
+    return out

@@ -8,16 +8,24 @@ reference; the work is done by libpgx_b200 on a B200:
 * ``compute_bernoulli_grid_core_genome`` (:101-166) -> scipy L-BFGS-B on the host driving
   the fp64 likelihood/gradient kernel (BernoulliGrid)
 
+* ``compute_beta_binomial_core_genome`` (:295-400), ``ks_montecarlo_bbn`` (:457-482) -> gene-frequency spectrum
+  counted on the GPU, scipy Nelder-Mead / Shapiro-Wilk on the host as in the reference, and the Monte-Carlo KS
+  simulation on the GPU (pgx_ks_montecarlo_host), consuming the global numpy RNG exactly as ``np.random.choice`` does
+
 Not provided (out of scope): the coordinate-descent variant the
-reference marks "DON'T USE THIS", the beta-binomial core estimate and the mlst wrapper.
+reference marks "DON'T USE THIS" and the mlst wrapper.
 """
 from __future__ import print_function
 
 import weakref
 
+import collections
+
 import numpy as np
 import pandas as pd
 import scipy.optimize
+import scipy.stats
+from scipy.special import betaln
 
 from .engine import BernoulliGrid, PanCoreEngine
 
@@ -198,3 +206,145 @@ def __bernoulli_grid_loglikelihood__(X, P, Q):
 def __bernoulli_grid_loglikelihood_gradient__(X, P, Q):
     ''' Gradient of the LL with respect to concat(P, Q) (GPU, fp64). '''
     return BernoulliGrid(X).gradient(np.asarray(P, dtype=np.float64), np.asarray(Q, dtype=np.float64))
+
+
+def compute_beta_binomial_core_genome(df_genes, frac_recovered=0.999, df_counts=None,
+                                      num_points=100, ks_iter=1000, device=None):
+    '''
+    Frequency threshold for core genes from an error-rate model: the number of genomes a core gene is
+    missing from is modelled as BetaBinomial(n_genomes, alpha, beta), fitted by maximum likelihood to the
+    ``num_points`` highest gene frequencies.
+
+    Parameters, return value (a Series for one ``num_points``, a DataFrame indexed by the number of points for a
+    list; entries alpha, beta, cutoff, mae, kolmogorov_smirnov_pvalue, shapiro_wilk_pvalue, durbin_watson_stat)
+    and the use of the global numpy RNG are those of the reference (:295-400).  ``df_genes`` may be the
+    reference's binary DataFrame with SparseArray columns or a LightSparseDataFrame (anything with a scipy
+    ``.data``); its gene-frequency spectrum is counted on the GPU and ordered by first appearance among the
+    genes, like the collections.Counter of :355.  The Monte-Carlo KS simulation runs on the GPU.
+    '''
+    if df_counts is None:
+        n_genes, n_genomes = df_genes.shape
+        df_counts = _gene_frequency_spectrum(df_genes, device)
+    else:
+        n_genomes = max(df_counts.index)
+
+    fitted = {}
+    fit_points = num_points if type(num_points) != int else [num_points]      # noqa: E721 (bool / np.int64 as in :359)
+    for n_points in fit_points:
+        # :364-366 -- the last n_points entries of the spectrum AS ORDERED, frequencies -> misses, reversed
+        tail = df_counts.iloc[-n_points:]
+        misses = n_genomes - tail.index
+        df = pd.Series(tail.values, index=misses).reindex(misses[::-1])
+        X = np.asarray(df.index)
+        Y = df.values
+
+        neg_ll = lambda ab: -np.dot(Y, betabin_logpmf(X, n_genomes, ab[0], ab[1]))      # noqa: E731
+        a, b = scipy.optimize.minimize(neg_ll, x0=(1, 100), method='Nelder-Mead').x
+
+        cutoff = 0
+        cdf = np.exp(betabin_logpmf(cutoff, n_genomes, a, b))
+        while cdf < frac_recovered:
+            cutoff += 1
+            cdf += np.exp(betabin_logpmf(cutoff, n_genomes, a, b))
+
+        residuals = np.asarray(Y - Y.sum() * np.exp(betabin_logpmf(X, n_genomes, a, b)))
+        mae = np.abs(residuals).mean()
+        sw_pvalue = scipy.stats.shapiro(residuals)[1]
+        dwstat = _durbin_watson(residuals)
+
+        model_cdf = np.cumsum(np.exp(betabin_logpmf(np.arange(n_genomes), n_genomes, a, b)))
+        sim_limit = np.where(1 - model_cdf < 1e-8)[0][0]           # simulate up to tolerance 1e-8 (:386)
+        if sim_limit > 0:
+            ks_pvalue = ks_montecarlo_bbn(df, n_genomes, a, b, iterations=ks_iter, sim_limit=sim_limit,
+                                          device=device)[0]
+        else:
+            ks_pvalue = np.nan
+        fitted[n_points] = pd.Series({
+            'alpha': a, 'beta': b, 'cutoff': cutoff, 'mae': mae,
+            'kolmogorov_smirnov_pvalue': ks_pvalue,
+            'shapiro_wilk_pvalue': sw_pvalue,
+            'durbin_watson_stat': dwstat})
+    table = pd.DataFrame.from_dict(fitted, orient='index')
+    return table.iloc[0, :] if table.shape[0] == 1 else table
+
+
+def _gene_frequency_spectrum(df_genes, device=None):
+    """{gene frequency: number of genes} as the reference builds it at :352-355 -- a collections.Counter over
+    the row sums, i.e. keyed in order of FIRST APPEARANCE among the genes -- from GPU counts."""
+    from . import sparse_utils
+    from .engine import table_marginals
+    data = df_genes.data if hasattr(df_genes, 'data') and hasattr(df_genes.data, 'tocoo') \
+        else sparse_utils.sparse_arrays_to_spmatrix(df_genes)
+    _, _, spectrum, first_gene = table_marginals(data, device=device)
+    present = np.flatnonzero(spectrum)
+    order = present[np.argsort(first_gene[present], kind='stable')]
+    return pd.Series(collections.OrderedDict((int(m), int(spectrum[m])) for m in order), dtype=np.int64)
+
+
+def _durbin_watson(residuals):
+    """statsmodels.stats.stattools.durbin_watson (:380) where statsmodels is installed, else its definition."""
+    try:
+        from statsmodels.stats.stattools import durbin_watson
+    except ImportError:
+        residuals = np.asarray(residuals, dtype=np.float64)
+        return float(np.sum(np.diff(residuals) ** 2) / np.sum(residuals ** 2))
+    return durbin_watson(residuals)
+
+
+def ks_montecarlo_bbn(Ycounts, n, a, b, iterations=100, sim_limit=1000, device=None):
+    '''
+    Monte-Carlo Kolmogorov-Smirnov test for a beta-binomial (:457-482): the KS statistic of the observed
+    counts against BBN(n, a, b) and its distribution under the model, simulated with ``iterations`` samples of
+    ``Ycounts.sum()`` draws each.  Returns (pvalue, ks_stat, ks_sim).  The draws come from the global numpy RNG
+    exactly as the reference's ``np.random.choice`` takes them; drawing, eCDFs and statistics run on the GPU.
+    '''
+    from .engine import ks_montecarlo_statistics
+    support = np.arange(sim_limit)
+    model_cdf = np.cumsum(np.exp(betabin_logpmf(support, n, a, b)))
+    ks_stat = np.max(np.abs(ecdf_from_counts(Ycounts.index, Ycounts.values, sim_limit) - model_cdf))
+
+    n_samples = Ycounts.sum()
+    iterations = int(iterations)
+    probs = _bbn_probabilities(n, a, b, sim_limit)
+    if n_samples * iterations <= 0:
+        ks_sim = np.full(max(iterations, 0), np.nan)               # the reference divides an empty eCDF by zero
+    else:
+        choice_cdf = probs.cumsum()                                # numpy legacy RandomState.choice
+        choice_cdf /= choice_cdf[-1]
+        ks_sim = ks_montecarlo_statistics(choice_cdf, model_cdf, n_samples, iterations, device=device)
+    pvalue = (ks_stat < ks_sim).sum() / float(iterations)
+    return pvalue, ks_stat, ks_sim
+
+
+def _bbn_probabilities(n, a, b, sim_limit):
+    """The probabilities draw_bbn hands to np.random.choice (:489-491), with numpy's own argument checks."""
+    probs = np.exp(betabin_logpmf(np.arange(sim_limit), n, a, b))
+    probs /= probs.sum()
+    if np.isnan(probs).any():
+        raise ValueError("probabilities contain NaN")
+    if (probs < 0).any():
+        raise ValueError("probabilities are not non-negative")
+    return probs
+
+
+def draw_bbn(n, a, b, size, sim_limit=1000):
+    '''
+    ``size`` draws from BBN(n, a, b) truncated to 0 .. sim_limit - 1 (:484-492), from the global numpy RNG.
+    '''
+    return np.random.choice(np.arange(sim_limit), size=size, p=_bbn_probabilities(n, a, b, sim_limit))
+
+
+def ecdf_from_counts(vals, counts, limit):
+    ''' eCDF on 0 .. limit - 1 from unique values and their counts (:494-499). '''
+    pmf = np.zeros(limit)
+    vals = np.asarray(vals)
+    if vals.size and (vals.max() >= limit or vals.min() < -limit):
+        raise IndexError('index %d is out of bounds for axis 0 with size %d' % (int(vals.max()), limit))
+    np.add.at(pmf, vals, counts)
+    return np.cumsum(pmf) / pmf.sum()
+
+
+def betabin_logpmf(x, n, a, b):
+    ''' Beta-binomial log-PMF (:501-508; scipy.stats.betabinom._logpmf). '''
+    k = np.floor(x)
+    return -np.log(n + 1) - betaln(n - k + 1, k + 1) + betaln(k + a, n - k + b) - betaln(a, b)

@@ -175,3 +175,31 @@ def bernoulli_grid_matrix(n_genes, n_genomes, seed=3):
     q = 1.0 - rng.beta(1.0, 60.0, size=n_genomes)
     x = (rng.random_sample((n_genes, n_genomes)) < np.outer(p, q)).astype(np.float64)
     return x, p, q
+
+
+def core_miss_spectrum(n_genomes=300, n_core=6000, a=0.6, b=90.0, n_accessory=1500, seed=11):
+    """Gene-frequency spectrum {frequency: number of genes} for the beta-binomial core estimate
+    (pangenome_analysis.py:295-400): ``n_core`` core genes whose miss counts follow BetaBinomial(n_genomes, a, b) --
+    the model the reference fits -- plus ``n_accessory`` accessory genes of uniform frequency.  Returned as the
+    arrays (frequencies ascending, counts > 0) a ``df_counts`` Series is made of."""
+    rng = np.random.RandomState(seed)
+    misses = rng.binomial(n_genomes, rng.beta(a, b, size=n_core))
+    freq = np.concatenate((n_genomes - misses, rng.randint(1, n_genomes + 1, size=n_accessory)))
+    freq = freq[freq >= 1]
+    counts = np.bincount(freq, minlength=n_genomes + 1)
+    keep = np.flatnonzero(counts)
+    return keep.astype(np.int64), counts[keep].astype(np.int64)
+
+
+def table_with_frequencies(freq, n_genomes, seed=0):
+    """Binary gene x genome COO table whose gene g is present in exactly ``freq[g]`` genomes chosen at random (rows
+    in the order given)."""
+    import scipy.sparse
+    rng = np.random.RandomState(seed)
+    freq = np.asarray(freq, dtype=np.int64)
+    rows, cols = [], []
+    for g, m in enumerate(freq):
+        cols.append(np.sort(rng.permutation(n_genomes)[:m]))
+        rows.append(np.full(m, g, dtype=np.int64))
+    rows, cols = np.concatenate(rows), np.concatenate(cols)
+    return scipy.sparse.coo_matrix((np.ones(rows.shape[0], dtype=np.int64), (rows, cols)), shape=(freq.shape[0], n_genomes))

@@ -5,6 +5,7 @@ Run in the build container only (the reference does not exist on the GPU box):
 
     python tests/golden/make_golden.py            # the round-1 fixtures
     python tests/golden/make_golden.py --big      # the full-size fixtures of round 2 (C2, C4, C3; ~3 min)
+    python tests/golden/make_golden.py --betabin  # beta-binomial core estimate, Monte-Carlo KS, gene occurrence
 
 The reference has no tests or golden vectors of its own, so
 these fixtures -- outputs of the unmodified reference functions under a fixed
@@ -34,8 +35,13 @@ REPO = os.path.dirname(os.path.dirname(HERE))
 sys.path.insert(0, REPO)
 sys.dont_write_bytecode = True
 sys.path.insert(0, "/root/reference")
-for name in ("statsmodels", "statsmodels.stats"):
+for name in ("statsmodels", "statsmodels.stats", "statsmodels.stats.stattools"):
     sys.modules.setdefault(name, types.ModuleType(name))
+sys.modules["statsmodels"].stats = sys.modules["statsmodels.stats"]
+sys.modules["statsmodels.stats"].stattools = sys.modules["statsmodels.stats.stattools"]
+# the one statsmodels function the reference calls (pangenome_analysis.py:380), by its textbook definition
+sys.modules["statsmodels.stats.stattools"].durbin_watson = \
+    lambda resids: float(np.sum(np.diff(resids) ** 2) / np.sum(np.asarray(resids) ** 2))
 
 import pangenomix.pangenome_analysis as ref_pa  # noqa: E402  (the reference)
 import pangenomix.sparse_utils as ref_su  # noqa: E402
@@ -161,7 +167,102 @@ def big_cases(manifest):
           "nfev", res.nfev, "%.1fs" % fit_seconds)
 
 
+def betabin_cases(manifest):
+    """Round-2 additions for SURVEY.md section 8(f) row 4: compute_beta_binomial_core_genome (pangenome_analysis.py:
+    295-400) and its Monte-Carlo KS test (:457-482) as the live reference computes them, together with every call of
+    ks_montecarlo_bbn they make (arguments and results recorded by a pass-through wrapper) and the state of the
+    global numpy RNG afterwards.  statsmodels is absent from the image: durbin_watson is the textbook formula."""
+    calls = []
+    original = ref_pa.ks_montecarlo_bbn
+
+    def recorder(ycounts, n, a, b, iterations=100, sim_limit=1000):
+        out = original(ycounts, n, a, b, iterations=iterations, sim_limit=sim_limit)
+        calls.append({"x": np.asarray(ycounts.index, dtype=np.int64), "y": np.asarray(ycounts.values, dtype=np.int64),
+                      "n": int(n), "a": float(a), "b": float(b), "iterations": int(iterations),
+                      "sim_limit": int(sim_limit), "pvalue": float(out[0]), "ks_stat": float(out[1]),
+                      "ks_sim": np.asarray(out[2], dtype=np.float64)})
+        return out
+
+    def run(name, df_genes, df_counts, num_points, ks_iter, seed, extra=None):
+        del calls[:]
+        ref_pa.ks_montecarlo_bbn = recorder
+        try:
+            np.random.seed(seed)
+            out = quiet(ref_pa.compute_beta_binomial_core_genome, df_genes, df_counts=df_counts,
+                        num_points=num_points, ks_iter=ks_iter)
+        finally:
+            ref_pa.ks_montecarlo_bbn = original
+        state = np.random.get_state()
+        table = out.to_frame().T if isinstance(out, pd.Series) else out
+        points = [num_points] if isinstance(num_points, int) else list(num_points)
+        store = {"num_points": np.asarray(points, dtype=np.int64), "single": np.bool_(isinstance(out, pd.Series)),
+                 "ks_iter": np.int64(ks_iter), "seed": np.int64(seed), "columns": np.array(list(table.columns)),
+                 "result": table.values.astype(np.float64), "n_ks_calls": np.int64(len(calls)),
+                 "rng_key_after": np.asarray(state[1], dtype=np.uint32), "rng_pos_after": np.int64(state[2])}
+        if df_counts is not None:
+            store["counts_index"] = np.asarray(df_counts.index, dtype=np.int64)
+            store["counts_values"] = np.asarray(df_counts.values, dtype=np.int64)
+        for i, call in enumerate(calls):
+            for key, value in call.items():
+                store["ks%d_%s" % (i, key)] = np.asarray(value)
+        store.update(extra or {})
+        np.savez_compressed(os.path.join(HERE, name + ".npz"), **store)
+        print("wrote", name, "points", points, "ks calls", len(calls))
+        print(table.to_string())
+
+    f, c = synth.core_miss_spectrum()
+    run("betabin_spectrum300", None, pd.Series(c, index=f), [10, 15, 25, 40], 200, 3)
+    f, c = synth.core_miss_spectrum(n_genomes=2000, n_core=40000, a=0.4, b=300.0, n_accessory=20000, seed=5)
+    run("betabin_spectrum2000", None, pd.Series(c, index=f), [15, 25, 40], 100, 4)
+    run("betabin_spectrum2000_single", None, pd.Series(c, index=f), 25, 60, 9)
+    # config C1's own spectrum (the reference's fit is poor there: p = 0)
+    c1 = synth.config_matrix("c1")
+    spectrum = np.bincount(np.bincount(c1.row, minlength=c1.shape[0]), minlength=c1.shape[1] + 1)
+    keep = np.flatnonzero(spectrum[1:]) + 1
+    run("betabin_c1", None, pd.Series(spectrum[keep].astype(np.int64), index=keep.astype(np.int64)), 10, 50, 12345)
+    # the df_genes path (:352-355): the spectrum is a collections.Counter of the row sums, i.e. ordered by FIRST
+    # APPEARANCE of each frequency among the rows, and ``iloc[-n_points:]`` (:364) takes the last of that order.
+    # (a) rows sorted by ascending frequency, so that the order is the sorted one; (b) rows as generated.
+    f, c = synth.core_miss_spectrum(n_genomes=60, n_core=3000, a=0.7, b=25.0, n_accessory=600, seed=21)
+    x = synth.table_with_frequencies(np.repeat(f, c), 60, seed=22)
+    index, columns = synth.labels_for(*x.shape)
+    dfs = pd.DataFrame.sparse.from_spmatrix(x.tocsc(), index=index, columns=columns)
+    run("betabin_table_sorted_3600x60", dfs, None, [10, 20], 80, 6,
+        extra={"row": x.row.astype(np.int32), "col": x.col.astype(np.int32), "shape": np.asarray(x.shape, dtype=np.int64)})
+    small = scipy.sparse.coo_matrix(synth.bernoulli_matrix(800, 50, 450, seed=7))
+    index, columns = synth.labels_for(*small.shape)
+    dfs = pd.DataFrame.sparse.from_spmatrix(small.tocsc(), index=index, columns=columns)
+    run("betabin_table_unsorted_800x50", dfs, None, 10, 40, 6,
+        extra={"row": small.row.astype(np.int32), "col": small.col.astype(np.int32),
+               "shape": np.asarray(small.shape, dtype=np.int64)})
+    # count_gene_occurence (core_genome.py:127-155) on the same table, read from the .npz the reference writes
+    import tempfile
+    bio = types.ModuleType("Bio")                 # core_genome.py:3 imports Bio.SeqIO (absent here, unused by the function)
+    bio.SeqIO = types.ModuleType("Bio.SeqIO")
+    sys.modules.setdefault("Bio", bio)
+    sys.modules.setdefault("Bio.SeqIO", bio.SeqIO)
+    import pangenomix.core_genome as ref_cg
+    with tempfile.TemporaryDirectory() as tmp:
+        path = os.path.join(tmp, "t.npz")
+        lsdf_of(small).to_npz(path)
+        occ = quiet(ref_cg.count_gene_occurence, path)
+    np.savez_compressed(os.path.join(HERE, "gene_occurence_800x50.npz"), gene_index=occ["gene_index"].values,
+                        count=occ["count"].values, columns=np.array(list(occ.columns)),
+                        row=small.row.astype(np.int32), col=small.col.astype(np.int32),
+                        shape=np.asarray(small.shape, dtype=np.int64))
+    print("wrote gene_occurence_800x50", occ.shape, occ.dtypes.to_dict())
+
+
 def main():
+    if "--betabin" in sys.argv:
+        path = os.path.join(HERE, "MANIFEST.json")
+        with open(path) as f:
+            manifest = json.load(f)
+        betabin_cases(manifest)
+        manifest["betabin"] = "statsmodels absent: durbin_watson = sum(diff(r)^2) / sum(r^2)"
+        with open(path, "w") as f:
+            json.dump(manifest, f, indent=1, sort_keys=True)
+        return
     if "--big" in sys.argv:
         path = os.path.join(HERE, "MANIFEST.json")
         with open(path) as f:
