@@ -27,6 +27,7 @@ configuration the north_star's roofline and scaling targets are quoted on.
   api   : the reference-facing Python call itself, estimate_pan_core_size(df, 2000): host RNG
           stream + H2D + kernels + D2H + float64 DataFrame.
   heaps : pgx_heaps_fit on the curves of one step next to scipy curve_fit.
+  beta_binomial : table marginals + compute_beta_binomial_core_genome with its Monte-Carlo KS on the GPU (8f rank 4).
 --workload c3 prints the same kind of line for the Bernoulli grid (LL + gradient evaluations/s,
 whole-fit time).  One JSON line on stdout (rank 0); everything else goes to stderr.
 """
@@ -538,6 +539,11 @@ def run_b200(args, rank, world, local_rank):
                  "note": "fit_heaps_by_iteration (scipy curve_fit, one host core) timed on 3 of the same curves; "
                          "results agree to 5e-6 relative (scipy's stopping tolerance)"}
 
+    # ---- last row of the scope table (8f rank 4): gene-frequency spectrum + beta-binomial core estimate ----
+    beta_binomial = None
+    if rank == 0 and not args.no_e2e:
+        beta_binomial = beta_binomial_entry(coo, check=not args.no_cpu_baseline)
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -645,10 +651,90 @@ def run_b200(args, rank, world, local_rank):
         "scaling": args.scaling, "vs_baseline": None, "dtype": "u16", "data": "synthetic", "config": config,
         "cells_per_s": value * n_genes * n, "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
         "gpu_launches": int(launches), "clocks": clocks, "host_rng_s_for_perms": host_rng_s, "api": api, "heaps": heaps,
+        "beta_binomial": beta_binomial,
     }
     emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def beta_binomial_entry(coo, check=True, num_points=25, ks_iter=1000):
+    """compute_beta_binomial_core_genome on the workload's table: the table's marginals and
+    gene-frequency spectrum counted on the GPU, then the fit with the reference's default 1,000 Monte-Carlo KS
+    iterations on the GPU.  With ``check`` the reference's own simulation loop (pangenome_analysis.py:471-480,
+    restated in oracle/betabin_np.py) is timed on a few iterations of the same stream and compared bit for bit."""
+    import warnings
+    import pandas as pd
+    from pangenomix_b200 import engine
+    from pangenomix_b200 import pangenome_analysis as pa
+    n_genes, n = coo.shape
+    try:
+        engine.table_marginals(coo)                                   # staging, first-call costs
+        t0 = time.perf_counter()
+        row_sum, col_sum, spectrum, _ = engine.table_marginals(coo)
+        marg_s = time.perf_counter() - t0
+        t0 = time.perf_counter()
+        want_row = np.asarray(coo.sum(axis=1)).ravel()
+        want_col = np.asarray(coo.sum(axis=0)).ravel()
+        scipy_s = time.perf_counter() - t0
+        assert np.array_equal(row_sum, want_row) and np.array_equal(col_sum, want_col)
+        freqs = np.flatnonzero(spectrum[1:]) + 1
+        counts = pd.Series(spectrum[freqs], index=freqs)                  # ascending gene frequency
+        calls = []
+        original = engine.ks_montecarlo_statistics
+
+        def timed(choice_cdf, model_cdf, n_samples, iterations, device=None):
+            state = np.random.get_state()
+            t = time.perf_counter()
+            out = original(choice_cdf, model_cdf, n_samples, iterations, device=device)
+            calls.append({"seconds": time.perf_counter() - t, "n_samples": int(n_samples), "iterations": int(iterations),
+                          "sim_limit": int(len(model_cdf)), "state": state, "cdf": choice_cdf, "model": model_cdf,
+                          "ks_sim": out})
+            return out
+
+        engine.ks_montecarlo_statistics = timed
+        try:
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                np.random.seed(12345)
+                pa.compute_beta_binomial_core_genome(None, df_counts=counts, num_points=num_points, ks_iter=8)   # staging
+                del calls[:]
+                np.random.seed(12345)
+                t0 = time.perf_counter()
+                fit = pa.compute_beta_binomial_core_genome(None, df_counts=counts, num_points=num_points, ks_iter=ks_iter)
+                fit_s = time.perf_counter() - t0
+        finally:
+            engine.ks_montecarlo_statistics = original
+        entry = {"call": "table_marginals + compute_beta_binomial_core_genome(df_counts=spectrum, num_points=%d, ks_iter=%d)"
+                         % (num_points, ks_iter),
+                 "marginals_ms": marg_s * 1e3, "scipy_sum_both_axes_ms": scipy_s * 1e3,
+                 "fit_seconds": fit_s, "fit": {k: (None if v != v else float(v)) for k, v in fit.items()}}
+        if calls:
+            c = calls[0]
+            draws = c["n_samples"] * c["iterations"]
+            entry.update({"ks_seconds": c["seconds"], "ks_draws": draws, "value": draws / c["seconds"], "unit": "draws/s",
+                          "ks_n_samples": c["n_samples"], "ks_sim_limit": c["sim_limit"]})
+            if check:
+                from oracle import betabin_np as ob
+                it_ref = max(2, min(c["iterations"], int(3e6 // max(1, c["n_samples"]))))
+                raw, _ = ob.raw_words(c["state"], 2 * c["n_samples"] * it_ref)
+                t0 = time.perf_counter()
+                draws_ref = np.asarray(c["cdf"]).searchsorted(ob.uniforms_from_raw(raw), side="right").reshape(it_ref, c["n_samples"])
+                ks_ref = np.zeros(it_ref)
+                for i in np.arange(it_ref):                                # the loop of :475-479, as written there
+                    vals, cnts = np.unique(draws_ref[i, :], return_counts=True)
+                    pmf = np.zeros(c["sim_limit"])
+                    for j in np.arange(len(vals)):
+                        pmf[vals[j]] += cnts[j]
+                    ks_ref[i] = np.max(np.abs(np.cumsum(pmf) / pmf.sum() - c["model"]))
+                ref_s = time.perf_counter() - t0
+                assert np.array_equal(c["ks_sim"][:it_ref], ks_ref)
+                entry["reference_loop"] = {"draws_per_s": c["n_samples"] * it_ref / ref_s, "iterations": it_ref, "kind": "port",
+                                           "note": "searchsorted + np.unique + eCDF loop per iteration on one host core, raw stream "
+                                                   "already drawn; first %d statistics identical to the GPU's" % it_ref}
+        return entry
+    except Exception as exc:                                         # noqa: BLE001 - an auxiliary entry never fails the bench
+        return {"error": "%s: %s" % (type(exc).__name__, exc)}
 
 
 # --------------------------------------------------------------------------------------

@@ -5,7 +5,7 @@
 //    sparse_utils.py:284-292 LightSparseDataFrame.sum; core_genome.py:127-155 count_gene_occurence):
 //    genes per genome, genomes per gene, and the gene-frequency spectrum {frequency: number of genes} together
 //    with the first gene of every frequency (a Counter is ordered by first appearance, and :364 slices that order).
-//    HBM-bound: 8 bytes per COO entry, one reduction per run of equal genes / genomes of a thread's stretch.
+//    8 bytes per COO entry, counted with warp-aggregated reductions; the host-buffer call is bound by PCIe.
 //
 // 2. The Monte-Carlo Kolmogorov-Smirnov statistics of ks_montecarlo_bbn (:457-482): ``iterations`` simulated samples
 //    of ``n_samples`` draws each from the fitted beta-binomial (draw_bbn :484-492 = numpy legacy
@@ -37,68 +37,41 @@ constexpr int COUNT_THREADS = 256;
 // ---------------------------------------------------------------------------------------------------------
 // marginals
 // ---------------------------------------------------------------------------------------------------------
-// Every thread owns a contiguous stretch of ENTRIES_PER_THREAD entries (16-byte loads; the stretch's lines stay in L1
-// between them) and adds a run of equal genes -- or genomes -- with ONE reduction: tables arrive sorted by gene or by
-// genome, and one reduction per entry would queue up to thousands of them on a single address in L2 (measured on
-// config C4, sorted by genome: 0.66 ms with warp-aggregated reductions, one address shared by 141 consecutive warps).
-constexpr int ENTRIES_PER_THREAD = 32;
-
-struct RunCounter {
-    int32_t *bins;
-    int limit, key = -1, run = 0, bad = 0;
-    __device__ RunCounter(int32_t *b, int l) : bins(b), limit(l) {}
-    __device__ __forceinline__ void add(int k)
-    {
-        if (k < 0 || k >= limit) {                      // outside the table: skipped and counted
-            flush();
-            key = -1;
-            ++bad;
-            return;
-        }
-        if (k == key) {
-            ++run;
-            return;
-        }
-        flush();
-        key = k;
-        run = 1;
-    }
-    __device__ __forceinline__ void flush()
-    {
-        if (run) atomicAdd(bins + key, run);
-        run = 0;
-    }
-};
+// One COO entry per lane and step (a warp reads 128 contiguous bytes of ``row`` and of ``col``); lanes holding the
+// same gene (or genome) elect a leader that adds their number with ONE reduction: tables arrive sorted by gene
+// or by genome, so an unaggregated warp would send 32 reductions to one address.  (A version in which every thread
+// run-length-counts a contiguous stretch of 32 entries was slower on config C4, 1.02 against 0.66 ms: the stretches of
+// a CTA's threads do not fit L1 together, and the scattered axis pays one reduction per entry either way.)
+__device__ __forceinline__ void aggregated_add(int32_t *bins, int key, bool valid)
+{
+    const unsigned active = __ballot_sync(FULL_MASK, valid);
+    if (!valid) return;
+    const unsigned same = __match_any_sync(active, key);
+    if ((__ffs(same) - 1) == static_cast<int>(threadIdx.x & 31)) atomicAdd(bins + key, __popc(same));
+}
 
 __global__ void __launch_bounds__(COUNT_THREADS)
 coo_count_kernel(const int32_t *__restrict__ row, const int32_t *__restrict__ col, long long nnz, int n_genes,
                  int n_genomes, int32_t *__restrict__ row_sum, int32_t *__restrict__ col_sum, int32_t *__restrict__ bad)
 {
-    const long long first = (static_cast<long long>(blockIdx.x) * COUNT_THREADS + threadIdx.x) * ENTRIES_PER_THREAD;
-    if (first >= nnz) return;
-    const long long last = min(nnz, first + ENTRIES_PER_THREAD);
-    RunCounter genes(row_sum, n_genes), genomes(col_sum, n_genomes);
-    // rows and cols may be 4-byte aligned only (slices of a larger array): vector loads when both are 16-byte aligned
-    const bool vec = ((reinterpret_cast<uintptr_t>(row) | reinterpret_cast<uintptr_t>(col)) & 15) == 0 &&
-                     last - first == ENTRIES_PER_THREAD;
-    if (vec) {
-        const int4 *r4 = reinterpret_cast<const int4 *>(row + first), *c4 = reinterpret_cast<const int4 *>(col + first);
-#pragma unroll 2
-        for (int i = 0; i < ENTRIES_PER_THREAD / 4; ++i) {
-            const int4 r = __ldg(r4 + i), c = __ldg(c4 + i);
-            genes.add(r.x); genes.add(r.y); genes.add(r.z); genes.add(r.w);
-            genomes.add(c.x); genomes.add(c.y); genomes.add(c.z); genomes.add(c.w);
+    const long long stride = static_cast<long long>(gridDim.x) * COUNT_THREADS;
+    const long long rounds = (nnz + stride - 1) / stride;                      // same trip count for the whole warp
+    long long i = static_cast<long long>(blockIdx.x) * COUNT_THREADS + threadIdx.x;
+    int n_bad = 0;
+    for (long long r = 0; r < rounds; ++r, i += stride) {
+        int g = -1, c = -1;
+        if (i < nnz) {
+            g = __ldg(row + i);
+            c = __ldg(col + i);
+            if (g < 0 || g >= n_genes || c < 0 || c >= n_genomes) {
+                g = c = -1;
+                ++n_bad;
+            }
         }
-    } else {
-        for (long long i = first; i < last; ++i) {
-            genes.add(__ldg(row + i));
-            genomes.add(__ldg(col + i));
-        }
+        aggregated_add(row_sum, g, g >= 0);
+        aggregated_add(col_sum, c, c >= 0);
     }
-    genes.flush();
-    genomes.flush();
-    // an entry outside the table on either axis is skipped on that axis only; the caller rejects the table anyway
-    if (genes.bad + genomes.bad) atomicAdd(bad, genes.bad + genomes.bad);
+    if (n_bad) atomicAdd(bad, n_bad);
 }
 
 __global__ void __launch_bounds__(COUNT_THREADS)
@@ -426,9 +399,11 @@ int pgx_coo_marginals(const int32_t *d_row, const int32_t *d_col, int64_t nnz, i
         PGX_CUDA(cudaMemsetAsync(d_bad, 0, sizeof(int32_t), st));
     }
     if (nnz == 0) return PGX_OK;
-    const long long per_cta = static_cast<long long>(pgx::COUNT_THREADS) * pgx::ENTRIES_PER_THREAD;
-    if (nnz > per_cta * 2147483647ll) return pgx::fail(PGX_ERR_UNSUPPORTED, "pgx_coo_marginals: too many entries for one call");
-    const unsigned grid = static_cast<unsigned>((nnz + per_cta - 1) / per_cta);
+    int dev = 0, sms = 0;
+    PGX_CUDA(cudaGetDevice(&dev));
+    PGX_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev));
+    const long long want = (nnz + pgx::COUNT_THREADS - 1) / pgx::COUNT_THREADS;
+    const unsigned grid = static_cast<unsigned>(std::min<long long>(want, 8ll * sms));
     pgx::coo_count_kernel<<<grid, pgx::COUNT_THREADS, 0, st>>>(d_row, d_col, nnz, n_genes, n_genomes, d_row_sum, d_col_sum, d_bad);
     PGX_LAUNCH_CHECK("coo_count_kernel");
     return PGX_OK;

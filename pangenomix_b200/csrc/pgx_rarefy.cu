@@ -89,6 +89,7 @@ struct Work {
     long long rank_stride;
     unsigned long long *trace = nullptr;      // optional CTA timeline (pgx_set_trace), null in normal operation
     long long trace_capacity = 0;
+    unsigned int *started = nullptr;          // optional: every list CTA counts itself here when it starts (probe gate)
 };
 
 // CTA timeline for the evidence of how the two row kernels share the SMs (scripts/overlap_trace.py): every CTA of the
@@ -438,6 +439,7 @@ list_kernel(const pgx_plan plan, const uint16_t *__restrict__ perms, const long 
     const uint4 *__restrict__ chunks = reinterpret_cast<const uint4 *>(plan.d_chunks);
     const int4 *__restrict__ tasks = reinterpret_cast<const int4 *>(plan.d_tasks);
     const unsigned long long t_start = work.trace ? global_timer() : 0ull;
+    if (work.started && tid == 0) atomicAdd(work.started, 1u);
 
     // Persistent CTAs: item = (batch of B permutations, share ``split`` of the tasks).  The whole
     // grid is resident at once, so CTAs of the probe kernel can fill the rest of every SM.
@@ -954,7 +956,7 @@ int list_variant()
 
 template <int B, bool P16>
 int launch_list(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm, const Work &work,
-                const DeviceLimits &lim, cudaStream_t stream)
+                const DeviceLimits &lim, cudaStream_t stream, unsigned *grid_out)
 {
     const int variant = list_variant();
     int threads = g_tuning.threads;
@@ -986,12 +988,13 @@ int launch_list(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm,
     const long long grid = max(1ll, min(n_items, static_cast<long long>(lim.sm_count) * max(1, per_sm)));
     kernel<<<static_cast<unsigned>(grid), threads, smem, stream>>>(plan, d_perms, n_perm, work, splits, n_items);
     PGX_LAUNCH_CHECK("list_kernel");
+    if (grid_out) *grid_out = static_cast<unsigned>(grid);
     return PGX_OK;
 }
 
 template <bool P16>
 int launch_list_b(const pgx_plan &plan, const uint16_t *d_perms, long long n_perm, const Work &work,
-                  const DeviceLimits &lim, cudaStream_t stream)
+                  const DeviceLimits &lim, cudaStream_t stream, unsigned *grid_out = nullptr)
 {
     const size_t per_perm = static_cast<size_t>(plan.n_genomes + SENTINELS) * sizeof(uint16_t);
     const size_t budget = static_cast<size_t>(lim.smem_optin) - 64 - 32 * EVENT_QUEUE * sizeof(uint32_t);
@@ -1001,10 +1004,10 @@ int launch_list_b(const pgx_plan &plan, const uint16_t *d_perms, long long n_per
     while (b > 1 && per_perm * b > budget) b >>= 1;
     if (per_perm * b > budget) return fail(PGX_ERR_UNSUPPORTED, "rank table does not fit shared memory");
     switch (b) {
-        case 8: return launch_list<8, P16>(plan, d_perms, n_perm, work, lim, stream);
-        case 4: return launch_list<4, P16>(plan, d_perms, n_perm, work, lim, stream);
-        case 2: return launch_list<2, P16>(plan, d_perms, n_perm, work, lim, stream);
-        default: return launch_list<1, P16>(plan, d_perms, n_perm, work, lim, stream);
+        case 8: return launch_list<8, P16>(plan, d_perms, n_perm, work, lim, stream, grid_out);
+        case 4: return launch_list<4, P16>(plan, d_perms, n_perm, work, lim, stream, grid_out);
+        case 2: return launch_list<2, P16>(plan, d_perms, n_perm, work, lim, stream, grid_out);
+        default: return launch_list<1, P16>(plan, d_perms, n_perm, work, lim, stream, grid_out);
     }
 }
 
@@ -1036,7 +1039,47 @@ struct Aux {
     int device = -1;
     cudaStream_t stream = nullptr;
     cudaEvent_t fork = nullptr, join = nullptr;
+    unsigned int *d_started = nullptr;        // list CTAs that have started, over all calls through this Aux
+    unsigned int expected = 0;                // ... and how many the host has launched
 };
+
+// The gate of the second stream.  The list kernel's CTAs need an SM whose shared-memory carve-out is at its maximum,
+// and an SM changes its carve-out only when it is empty: if the probe kernel's small CTAs get to the SMs first -- as
+// in a call that finds the device idle -- every list CTA waits until its SM has drained and the two kernels run one
+// after the other (9.0 instead of 7.6 ms per 10,000 permutations of C4).  So the probe launch waits, IN THE STREAM
+// (cuStreamWaitValue32: no CTA is resident while it waits -- a spinning gate kernel blocks the carve-out change of
+// its own SM, measured), until every list CTA of the call has counted itself in Aux::d_started.
+// PGX_PROBE_GATE=0 switches the gate off.
+typedef int (*StreamWaitValue32)(cudaStream_t, unsigned long long, unsigned int, unsigned int);
+
+StreamWaitValue32 stream_wait_value32()
+{
+    static const StreamWaitValue32 fn = [] {
+        const char *env = getenv("PGX_PROBE_GATE");
+        if (env && atoi(env) == 0) return static_cast<StreamWaitValue32>(nullptr);
+        void *entry = nullptr;
+        cudaDriverEntryPointQueryResult status;
+        if (cudaGetDriverEntryPoint("cuStreamWaitValue32", &entry, cudaEnableDefault, &status) != cudaSuccess ||
+            status != cudaDriverEntryPointSuccess) {
+            cudaGetLastError();
+            return static_cast<StreamWaitValue32>(nullptr);
+        }
+        return reinterpret_cast<StreamWaitValue32>(entry);
+    }();
+    return fn;
+}
+
+int aux_init(Aux &a, int dev)
+{
+    PGX_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
+    PGX_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
+    PGX_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
+    PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&a.d_started), sizeof(unsigned int)));
+    PGX_CUDA(cudaMemset(a.d_started, 0, sizeof(unsigned int)));
+    a.expected = 0;
+    a.device = dev;
+    return PGX_OK;
+}
 
 int aux_for_device(Aux **out)
 {
@@ -1046,10 +1089,7 @@ int aux_for_device(Aux **out)
     if (dev < 0 || dev >= 64) return fail(PGX_ERR_UNSUPPORTED, "device ordinal %d out of range", dev);
     Aux &a = aux[dev];
     if (a.device != dev) {
-        PGX_CUDA(cudaStreamCreateWithFlags(&a.stream, cudaStreamNonBlocking));
-        PGX_CUDA(cudaEventCreateWithFlags(&a.fork, cudaEventDisableTiming));
-        PGX_CUDA(cudaEventCreateWithFlags(&a.join, cudaEventDisableTiming));
-        a.device = dev;
+        if (int rc = aux_init(a, dev)) return rc;
     }
     *out = &a;
     return PGX_OK;
@@ -1110,12 +1150,21 @@ int run_rows(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, co
         PGX_CUDA(cudaEventRecord(aux->fork, stream));
         PGX_CUDA(cudaStreamWaitEvent(aux->stream, aux->fork, 0));
     }
+    const StreamWaitValue32 gate = overlap && aux->d_started ? stream_wait_value32() : nullptr;
+    unsigned list_grid = 0;
     if (plan->n_tasks > 0) {
-        if (int rc = launch_list_b<P16>(*plan, d_perms, n_perm, work, lim, stream)) return rc;
+        if (gate) work.started = aux->d_started;
+        if (int rc = launch_list_b<P16>(*plan, d_perms, n_perm, work, lim, stream, &list_grid)) return rc;
     }
     if (ev) PGX_CUDA(cudaEventRecord(ev->list_done, stream));
     if (overlap) {
         // launched AFTER the list kernel: one list CTA per SM first, probe CTAs fill what is left
+        if (gate) {
+            aux->expected += list_grid;
+            // CU_STREAM_WAIT_VALUE_GEQ (0): until (int32_t)(*addr - value) >= 0, i.e. cyclic like the counter
+            const int err = gate(aux->stream, reinterpret_cast<unsigned long long>(aux->d_started), aux->expected, 0u);
+            if (err != 0) return fail(PGX_ERR_CUDA, "cuStreamWaitValue32 failed with driver error %d", err);
+        }
         if (int rc = launch_probe<P16>(*plan, d_perms, n_perm, work, aux->stream)) return rc;
         PGX_CUDA(cudaEventRecord(aux->join, aux->stream));
         PGX_CUDA(cudaStreamWaitEvent(stream, aux->join, 0));
@@ -1240,6 +1289,7 @@ void release(Pipe &b)
         if (s.aux.stream) cudaStreamDestroy(s.aux.stream);
         if (s.aux.fork) cudaEventDestroy(s.aux.fork);
         if (s.aux.join) cudaEventDestroy(s.aux.join);
+        if (s.aux.d_started) cudaFree(s.aux.d_started);
         s = Slot{};
     }
     if (b.bad_rows) cudaFreeHost(b.bad_rows);
@@ -1259,10 +1309,7 @@ int acquire(Pipe &b, int device, long long block, long long n, bool packed, bool
     for (auto &s : b.slot) {
         PGX_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
         PGX_CUDA(cudaEventCreateWithFlags(&s.done, cudaEventDisableTiming));
-        PGX_CUDA(cudaStreamCreateWithFlags(&s.aux.stream, cudaStreamNonBlocking));
-        PGX_CUDA(cudaEventCreateWithFlags(&s.aux.fork, cudaEventDisableTiming));
-        PGX_CUDA(cudaEventCreateWithFlags(&s.aux.join, cudaEventDisableTiming));
-        s.aux.device = device;
+        if (int rc = aux_init(s.aux, device)) return rc;
         if (rng) PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s.h_perm), sizeof(uint16_t) * block * n, cudaHostAllocDefault));
         PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_perm), sizeof(uint16_t) * block * n));
         if (packed) {

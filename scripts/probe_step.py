@@ -1,4 +1,4 @@
-"""Back-to-back steps of the device-resident call, timed as bench.py times them (development aid).
+"""Back-to-back steps of the device-resident call, timed as bench.py times them, and isolated calls (development aid).
 
     [PGX_... env] python scripts/probe_step.py c4 10000 [steps]
 """
@@ -29,6 +29,16 @@ for _ in range(steps):
 e1.record()
 torch.cuda.synchronize()
 ms = e0.elapsed_time(e1) / steps
+# isolated calls: the device idle before and after every call
+isolated = []
+for _ in range(9):
+    torch.cuda.synchronize()
+    e0.record()
+    eng.curves_device(d_perms, out=out)
+    e1.record()
+    torch.cuda.synchronize()
+    isolated.append(e0.elapsed_time(e1))
+iso = sorted(isolated)[len(isolated) // 2]
 _native.profile_read()
 _native.profile_enable(True)
 for _ in range(3):
@@ -37,5 +47,5 @@ torch.cuda.synchronize()
 a, b, c, calls = _native.profile_read()
 _native.profile_enable(False)
 env = " ".join("%s=%s" % kv for kv in sorted(os.environ.items()) if kv[0].startswith("PGX_"))
-print("%s %d perms [%s]: step %.3f ms (%.0f perms/s); serialised: list %.3f probe %.3f prep+scan %.3f ms" % (
-    name, n_perm, env, ms, n_perm / ms * 1e3, a / calls, b / calls, c / calls), flush=True)
+print("%s %d perms [%s]: step %.3f ms (%.0f perms/s), isolated call %.3f ms; serialised: list %.3f probe %.3f prep+scan %.3f ms" % (
+    name, n_perm, env, ms, n_perm / ms * 1e3, iso, a / calls, b / calls, c / calls), flush=True)
