@@ -196,7 +196,7 @@ int pgx_profile_read(double *list_ms, double *probe_ms, double *scan_ms, int64_t
 /* Evidence of how the two row kernels share the SMs: while a device buffer of 1 + 3 * capacity_records uint64 is set
  * (zero-initialised by the caller; null switches the trace off), every CTA of the list kernel and every warp of the
  * probe kernel appends {kind (1 list, 2 probe) | smid << 8, start, end} in %globaltimer nanoseconds; word 0 counts
- * the records.  scripts/overlap_trace.py turns it into profiles/*_overlap_timeline.json. */
+ * the records.  scripts/overlap_trace.py turns it into profiles/r02/overlap_timeline_<name>.json. */
 int pgx_set_trace(void *d_trace, int64_t capacity_records);
 
 /* Number of kernels this library has launched since load (bench.py's gpu_launches). */

@@ -67,10 +67,63 @@ int main(int argc, char **argv)
             }
         }
     }
+    /* marginals of the table (pangenome_analysis.py:354-355) against the dense copy */
+    {
+        static int32_t row_sum[G], col_sum[N], first_gene[N + 1];
+        static int64_t spectrum[N + 1];
+        if (pgx_coo_marginals_host(row, col, nnz, G, N, row_sum, col_sum, spectrum, first_gene)) { fprintf(stderr, "marginals: %s\n", pgx_last_error()); return 1; }
+        int64_t want_spectrum[N + 1] = {0};
+        for (int g = 0; g < G; ++g) {
+            int m = 0;
+            for (int c = 0; c < N; ++c) m += x[g][c];
+            if (row_sum[g] != m) { fprintf(stderr, "row sum of gene %d: got %d, want %d\n", g, row_sum[g], m); return 1; }
+            ++want_spectrum[m];
+        }
+        for (int c = 0; c < N; ++c) {
+            int m = 0;
+            for (int g = 0; g < G; ++g) m += x[g][c];
+            if (col_sum[c] != m) { fprintf(stderr, "column sum of genome %d: got %d, want %d\n", c, col_sum[c], m); return 1; }
+        }
+        for (int m = 0; m <= N; ++m) {
+            if (spectrum[m] != want_spectrum[m]) { fprintf(stderr, "spectrum[%d]: got %lld, want %lld\n", m, (long long)spectrum[m], (long long)want_spectrum[m]); return 1; }
+            if (spectrum[m] && row_sum[first_gene[m]] != m) { fprintf(stderr, "first gene of frequency %d is wrong\n", m); return 1; }
+        }
+    }
+    /* Monte-Carlo KS statistics (pangenome_analysis.py:471-480) against the definition, from the same raw words */
+    {
+        enum { BINS = 9, SAMPLES = 777, ITER = 13 };
+        double cdf[BINS], ks[ITER];
+        for (int k = 0; k < BINS; ++k) cdf[k] = 1.0 - 1.0 / (double)(1 << (k + 1));
+        cdf[BINS - 1] = 1.0;
+        static uint32_t key[624], key2[624], raw[2 * SAMPLES * ITER];
+        for (int k = 0; k < 624; ++k) key[k] = key2[k] = next_u32();
+        int32_t pos = 17, pos2 = 17;
+        if (pgx_ks_montecarlo_host(key, &pos, ITER, SAMPLES, cdf, cdf, BINS, ks)) { fprintf(stderr, "ks: %s\n", pgx_last_error()); return 1; }
+        if (pgx_legacy_random_raw(key2, &pos2, 2 * SAMPLES * ITER, raw)) { fprintf(stderr, "raw: %s\n", pgx_last_error()); return 1; }
+        if (pos != pos2 || memcmp(key, key2, sizeof(key))) { fprintf(stderr, "ks: the stream did not advance by 2 words per draw\n"); return 1; }
+        for (int it = 0; it < ITER; ++it) {
+            int hist[BINS] = {0};
+            for (int s = 0; s < SAMPLES; ++s) {
+                const uint32_t a = raw[2 * (it * SAMPLES + s)] >> 5, b = raw[2 * (it * SAMPLES + s) + 1] >> 6;
+                const double u = (a * 67108864.0 + b) / 9007199254740992.0;
+                int idx = 0;
+                while (idx < BINS && cdf[idx] <= u) ++idx;
+                ++hist[idx];
+            }
+            double worst = 0.0;
+            long long cum = 0;
+            for (int k = 0; k < BINS; ++k) {
+                cum += hist[k];
+                const double d = (double)cum / (double)SAMPLES - cdf[k];
+                if ((d < 0 ? -d : d) > worst) worst = d < 0 ? -d : d;
+            }
+            if (ks[it] != worst) { fprintf(stderr, "ks statistic %d: got %.17g, want %.17g\n", it, ks[it], worst); return 1; }
+        }
+    }
     /* the second entry point: plan and upload in one call */
     pgx_plan *again = NULL;
     if (pgx_plan_create(row, col, nnz, G, N, -1, &again) || pgx_plan_destroy(again)) { fprintf(stderr, "create: %s\n", pgx_last_error()); return 1; }
     if (pgx_plan_destroy(plan)) return 1;
-    printf("gpu ok: %d curves bit-exact\n", PERMS);
+    printf("gpu ok: %d curves, the marginals and %d KS statistics bit-exact\n", PERMS, 13);
     return 0;
 }

@@ -340,6 +340,41 @@ def test_gpu_marginals_match_numpy(cuda, table):
 
 
 @pytest.mark.gpu
+def test_gpu_marginals_device_pointer_calls(cuda):
+    """pgx_coo_marginals in two chunks (accumulate) + pgx_frequency_spectrum on caller-owned device buffers; entries
+    outside the table are skipped and counted."""
+    torch = cuda
+    lib = _native.load()
+    coo = synth.bernoulli_matrix(2000, 90, 450, seed=8).tocoo()
+    row = np.ascontiguousarray(coo.row, dtype=np.int32).copy()
+    col = np.ascontiguousarray(coo.col, dtype=np.int32).copy()
+    row[5], col[11] = 2000, -1                                  # two entries outside the table
+    good = np.ones(row.shape[0], dtype=bool)
+    good[[5, 11]] = False
+    d_row, d_col = torch.from_numpy(row).cuda(), torch.from_numpy(col).cuda()
+    d_rs = torch.empty(2000, dtype=torch.int32, device="cuda")
+    d_cs = torch.empty(90, dtype=torch.int32, device="cuda")
+    d_bad = torch.empty(1, dtype=torch.int32, device="cuda")
+    d_spec = torch.empty(91, dtype=torch.int64, device="cuda")
+    d_first = torch.empty(91, dtype=torch.int32, device="cuda")
+    stream = torch.cuda.current_stream().cuda_stream
+    half = 4 * (row.shape[0] // 8) + 1                          # the second chunk starts on a 4-byte boundary only
+    _native.check(lib.pgx_coo_marginals(d_row.data_ptr(), d_col.data_ptr(), half, 2000, 90, d_rs.data_ptr(), d_cs.data_ptr(),
+                                        d_bad.data_ptr(), 0, stream))
+    _native.check(lib.pgx_coo_marginals(d_row.data_ptr() + 4 * half, d_col.data_ptr() + 4 * half, row.shape[0] - half, 2000, 90,
+                                        d_rs.data_ptr(), d_cs.data_ptr(), d_bad.data_ptr(), 1, stream))
+    _native.check(lib.pgx_frequency_spectrum(d_rs.data_ptr(), 2000, 90, d_spec.data_ptr(), d_first.data_ptr(), stream))
+    want_row = np.bincount(row[good], minlength=2000)
+    assert int(d_bad.item()) == 2
+    assert np.array_equal(d_rs.cpu().numpy(), want_row)
+    assert np.array_equal(d_cs.cpu().numpy(), np.bincount(col[good], minlength=90))
+    spectrum, first = d_spec.cpu().numpy(), d_first.cpu().numpy()
+    assert np.array_equal(spectrum, np.bincount(want_row, minlength=91))
+    present = np.flatnonzero(spectrum)
+    assert [int(m) for m in present[np.argsort(first[present], kind="stable")]] == _counter_order(want_row)
+
+
+@pytest.mark.gpu
 def test_gpu_marginals_reject_bad_tables(cuda):
     bad = scipy.sparse.coo_matrix((np.ones(2, dtype=np.int64), ([0, 1], [0, 1])), shape=(2, 2))
     bad.row = bad.row.copy()
