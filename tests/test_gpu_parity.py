@@ -395,7 +395,32 @@ def test_c_host_program_end_to_end(engine_mod, tmp_path):
     exe = _build_c_host(tmp_path)
     run = subprocess.run([exe, "--gpu"], capture_output=True, text=True)
     assert run.returncode == 0, run.stdout + run.stderr
-    assert "gpu ok: 21 curves bit-exact" in run.stdout
+    assert "gpu ok: 21 curves, the marginals and 13 KS statistics bit-exact" in run.stdout
+
+
+def test_probe_gate_off_gives_the_same_curves(engine_mod):
+    """PGX_PROBE_GATE=0 (read once per process, hence a child process): without the stream-level wait before the
+    probe launch the two row kernels may start in either order; the curves must not depend on it."""
+    import os
+    import subprocess
+    import sys
+    from conftest import REPO
+    code = (
+        "import sys, numpy as np; sys.path.insert(0, %r); sys.path.insert(0, %r)\n"
+        "import oracle\n"
+        "from conftest import draw_perms\n"
+        "from pangenomix_b200 import engine, synth\n"
+        "coo = synth.bernoulli_matrix(6000, 900, 450, seed=5)\n"
+        "eng = engine.PanCoreEngine(coo)\n"
+        "assert eng.host_plan.n_long > 0 and eng.host_plan.n_rows > 0\n"
+        "perms = draw_perms(4, 900, 37)\n"
+        "pan, core = oracle.pan_core_curves_minrank(coo, perms)\n"
+        "for _ in range(3):\n"
+        "    assert np.array_equal(eng.curves_host(perms.astype(np.uint16)), np.hstack([pan, core]).astype(np.int32))\n"
+        "print('gate off ok')\n" % (REPO, os.path.join(REPO, "tests")))
+    env = dict(os.environ, PGX_PROBE_GATE="0")
+    run = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, env=env, timeout=600)
+    assert run.returncode == 0 and "gate off ok" in run.stdout, run.stdout + run.stderr
 
 
 def test_rows_that_are_not_permutations_are_reported(engine_mod):
