@@ -32,6 +32,7 @@ namespace pgx {
 namespace {
 
 constexpr int KS_THREADS = 256;
+constexpr int KS_UNROLL = 4;
 constexpr int COUNT_THREADS = 256;
 
 // ---------------------------------------------------------------------------------------------------------
@@ -124,11 +125,13 @@ __device__ __forceinline__ int upper_bound(const double *cdf, int len, double u)
 // ``in_smem`` the choice CDF and the histogram live in shared memory (sim_limit * 12 bytes); otherwise the CDF is
 // read through L1/L2 and the histogram is the iteration's row of ``g_hist`` (zeroed by the caller).  When an
 // iteration is split, every CTA adds its bins to ``g_hist`` and the last one to arrive (ticket) finishes it.
+template <bool IN_SMEM>
 __global__ void __launch_bounds__(KS_THREADS)
 ks_kernel(const uint2 *__restrict__ raw, long long n_samples, long long per_split, const double *__restrict__ choice_cdf,
-          const double *__restrict__ model_cdf, int sim_limit, int in_smem, int32_t *__restrict__ g_hist,
+          const double *__restrict__ model_cdf, int sim_limit, int32_t *__restrict__ g_hist,
           int32_t *__restrict__ tickets, double *__restrict__ ks_sim)
 {
+    constexpr bool in_smem = IN_SMEM;          // a template parameter: the shared-memory instance gets LDS / ATOMS, not generic accesses
     extern __shared__ __align__(16) unsigned char smem_raw[];
     __shared__ long long seg_sum[KS_THREADS];
     __shared__ double warp_max[KS_THREADS / 32];
@@ -138,15 +141,11 @@ ks_kernel(const uint2 *__restrict__ raw, long long n_samples, long long per_spli
     double *s_cdf = reinterpret_cast<double *>(smem_raw);
     int32_t *s_hist = reinterpret_cast<int32_t *>(s_cdf + sim_limit);
     int32_t *row_hist = g_hist ? g_hist + static_cast<long long>(it) * sim_limit : nullptr;
-    const double *cdf = choice_cdf;
-    int32_t *hist = row_hist;
-    if (in_smem) {
+    if constexpr (in_smem) {
         for (int k = tid; k < sim_limit; k += KS_THREADS) {
             s_cdf[k] = __ldg(choice_cdf + k);
             s_hist[k] = 0;
         }
-        cdf = s_cdf;
-        hist = s_hist;
         __syncthreads();
     }
 
@@ -154,29 +153,41 @@ ks_kernel(const uint2 *__restrict__ raw, long long n_samples, long long per_spli
     const long long s0 = static_cast<long long>(blockIdx.x) * per_split;
     const long long s1 = min(n_samples, s0 + per_split);
     const uint2 *src = raw + static_cast<long long>(it) * n_samples;
-    const long long rounds = (max(s1 - s0, 0ll) + KS_THREADS - 1) / KS_THREADS;
+    // KS_UNROLL draws per thread and round: their loads are issued together (one 8-byte load in flight per thread left
+    // the kernel waiting on the long scoreboard, ncu capture r02q)
+    const long long rounds = (max(s1 - s0, 0ll) + KS_THREADS * KS_UNROLL - 1) / (KS_THREADS * KS_UNROLL);
     long long s = s0 + tid;
-    for (long long r = 0; r < rounds; ++r, s += KS_THREADS) {
-        const bool valid = s < s1;
-        int idx = 0;
-        if (valid) {
-            const uint2 w = __ldcs(src + s);                                  // read once: streaming
-            const double u = (static_cast<double>(w.x >> 5) * 67108864.0 + static_cast<double>(w.y >> 6)) *
-                             (1.0 / 9007199254740992.0);                       // exact: a power of two
-            idx = min(upper_bound(cdf, sim_limit, u), sim_limit - 1);
-        }
-        // most draws fall into the first few bins (a core gene is rarely missing): aggregate equal bins per warp
-        const unsigned active = __ballot_sync(FULL_MASK, valid);
-        if (valid) {
-            const unsigned same = __match_any_sync(active, idx);
-            if ((__ffs(same) - 1) == lane) atomicAdd(hist + idx, __popc(same));
+    for (long long r = 0; r < rounds; ++r, s += KS_THREADS * KS_UNROLL) {
+        uint2 w[KS_UNROLL];
+#pragma unroll
+        for (int j = 0; j < KS_UNROLL; ++j)
+            w[j] = s + j * KS_THREADS < s1 ? __ldcs(src + s + j * KS_THREADS) : make_uint2(0u, 0u);      // read once: streaming
+#pragma unroll
+        for (int j = 0; j < KS_UNROLL; ++j) {
+            const bool valid = s + j * KS_THREADS < s1;
+            int idx = 0;
+            if (valid) {
+                const double u = (static_cast<double>(w[j].x >> 5) * 67108864.0 + static_cast<double>(w[j].y >> 6)) *
+                                 (1.0 / 9007199254740992.0);                   // exact: a power of two
+                if constexpr (in_smem) idx = min(upper_bound(s_cdf, sim_limit, u), sim_limit - 1);
+                else idx = min(upper_bound(choice_cdf, sim_limit, u), sim_limit - 1);
+            }
+            // most draws fall into the first few bins (a core gene is rarely missing): aggregate equal bins per warp
+            const unsigned active = __ballot_sync(FULL_MASK, valid);
+            if (valid) {
+                const unsigned same = __match_any_sync(active, idx);
+                if ((__ffs(same) - 1) == lane) {
+                    if constexpr (in_smem) atomicAdd(s_hist + idx, __popc(same));
+                    else atomicAdd(row_hist + idx, __popc(same));
+                }
+            }
         }
     }
     __syncthreads();
 
     // ---- hand-over when the iteration is split ------------------------------------------------------------
     if (splits > 1) {
-        if (in_smem)
+        if constexpr (in_smem)
             for (int k = tid; k < sim_limit; k += KS_THREADS)
                 if (s_hist[k]) atomicAdd(row_hist + k, s_hist[k]);
         __threadfence();
@@ -185,19 +196,21 @@ ks_kernel(const uint2 *__restrict__ raw, long long n_samples, long long per_spli
         __syncthreads();
         if (!is_last) return;
         __threadfence();
-        if (in_smem) {
+        if constexpr (in_smem) {
             for (int k = tid; k < sim_limit; k += KS_THREADS) s_hist[k] = __ldcg(row_hist + k);
             __syncthreads();
-        } else {
-            hist = row_hist;
         }
     }
+    auto bin = [&](int k) -> long long {
+        if constexpr (in_smem) return s_hist[k];
+        else return __ldcg(row_hist + k);
+    };
 
     // ---- eCDF and KS statistic (:475-479): cumsum(pmf) / pmf.sum(), max |. - model_cdf| ------------------------
     const int seg = (sim_limit + KS_THREADS - 1) / KS_THREADS;
     const int k0 = min(tid * seg, sim_limit), k1 = min(k0 + seg, sim_limit);
     long long local = 0;
-    for (int k = k0; k < k1; ++k) local += in_smem ? hist[k] : __ldcg(hist + k);
+    for (int k = k0; k < k1; ++k) local += bin(k);
     seg_sum[tid] = local;
     __syncthreads();
     long long before = 0;
@@ -206,7 +219,7 @@ ks_kernel(const uint2 *__restrict__ raw, long long n_samples, long long per_spli
     double worst = 0.0;
     bool nan_seen = false;
     for (int k = k0; k < k1; ++k) {
-        before += in_smem ? hist[k] : __ldcg(hist + k);
+        before += bin(k);
         const double d = fabs(static_cast<double>(before) / total - __ldg(model_cdf + k));
         nan_seen |= d != d;
         worst = fmax(worst, d);
@@ -266,11 +279,15 @@ int ks_launch(const uint32_t *d_raw, int64_t iterations, int64_t n_samples, cons
     if (shape.smem_bytes > 48 * 1024) {
         static std::mutex mu;
         std::lock_guard<std::mutex> lock(mu);
-        PGX_CUDA(cudaFuncSetAttribute(ks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shape.smem_bytes)));
+        PGX_CUDA(cudaFuncSetAttribute(ks_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(shape.smem_bytes)));
     }
-    ks_kernel<<<dim3(static_cast<unsigned>(shape.splits), static_cast<unsigned>(iterations)), KS_THREADS, shape.smem_bytes, st>>>(
-        reinterpret_cast<const uint2 *>(d_raw), n_samples, shape.per_split, d_choice_cdf, d_model_cdf, sim_limit,
-        shape.in_smem, g_hist, tickets, d_ks_sim);
+    const dim3 grid(static_cast<unsigned>(shape.splits), static_cast<unsigned>(iterations));
+    if (shape.in_smem)
+        ks_kernel<true><<<grid, KS_THREADS, shape.smem_bytes, st>>>(reinterpret_cast<const uint2 *>(d_raw), n_samples, shape.per_split,
+                                                                    d_choice_cdf, d_model_cdf, sim_limit, g_hist, tickets, d_ks_sim);
+    else
+        ks_kernel<false><<<grid, KS_THREADS, 0, st>>>(reinterpret_cast<const uint2 *>(d_raw), n_samples, shape.per_split,
+                                                      d_choice_cdf, d_model_cdf, sim_limit, g_hist, tickets, d_ks_sim);
     PGX_LAUNCH_CHECK("ks_kernel");
     return PGX_OK;
 }
@@ -315,10 +332,12 @@ int ks_acquire(KsStage &s, int device, size_t raw_bytes, size_t cdf_len, size_t 
     if (s.device == device && s.raw_bytes >= raw_bytes && s.cdf_len >= cdf_len && s.sim_len >= sim_len &&
         s.scratch_bytes >= scratch_bytes)
         return PGX_OK;
-    raw_bytes = std::max(raw_bytes, s.device == device ? s.raw_bytes : 0);
-    cdf_len = std::max(cdf_len, s.device == device ? s.cdf_len : 0);
-    sim_len = std::max(sim_len, s.device == device ? s.sim_len : 0);
-    scratch_bytes = std::max(scratch_bytes, s.device == device ? s.scratch_bytes : 0);
+    // generous floors: a fit calls this with a few iterations first and with thousands later, and re-pinning the
+    // staging costs more than the whole simulation (16 ms against 2 ms, measured)
+    raw_bytes = std::max<size_t>(std::max(raw_bytes, s.device == device ? s.raw_bytes : 0), 32u << 20);
+    cdf_len = std::max<size_t>(std::max(cdf_len, s.device == device ? s.cdf_len : 0), 4096);
+    sim_len = std::max<size_t>(std::max(sim_len, s.device == device ? s.sim_len : 0), 65536);
+    scratch_bytes = std::max<size_t>(std::max(scratch_bytes, s.device == device ? s.scratch_bytes : 0), 8u << 20);
     ks_release(s);
     PGX_CUDA(cudaStreamCreateWithFlags(&s.stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {

@@ -64,7 +64,8 @@ def main():
                     pass
             kind = short
             for key, tag_ in (("list_kernel", "list"), ("probe_kernel", "probe"), ("scan_kernel", "scan"), ("prep_scatter_kernel", "prep"),
-                              ("prep_kernel", "prep"), ("grid_kernel", "grid"), ("finish_kernel", "finish"), ("heaps_kernel", "heaps")):
+                              ("prep_kernel", "prep"), ("grid_kernel", "grid"), ("finish_kernel", "finish"), ("heaps_kernel", "heaps"),
+                              ("ks_kernel", "ks"), ("coo_count_kernel", "coo_count"), ("spectrum_kernel", "spectrum")):
                 if key in name:
                     kind = tag_
                     break
