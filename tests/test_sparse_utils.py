@@ -182,3 +182,22 @@ def test_read_lsdf_uses_the_native_decoder_and_falls_back(tmp_path, monkeypatch)
     wrong = lambda raw, size: np.zeros(size, dtype=np.uint8)                        # a wrong answer fails the CRC
     monkeypatch.setattr(su, "_native_inflate", wrong)
     assert (su.read_lsdf(path).data.tocsr() != coo.tocsr()).nnz == 0
+
+
+def test_reference_import_paths_resolve_to_the_drop_in():
+    """Both import styles of the reference (README.md:146 top-level modules inside the package directory,
+    pangenome_analysis.py:22 ``import pangenomix.sparse_utils``) reach the B200 implementation."""
+    import importlib
+    import pangenomix_b200.core_genome
+    import pangenomix_b200.pangenome_analysis
+    import pangenomix_b200.plot
+    import pangenomix_b200.sparse_utils
+    for name in ("sparse_utils", "pangenome_analysis", "plot", "core_genome"):
+        shim = importlib.import_module("pangenomix." + name)
+        assert shim is getattr(pangenomix_b200, name)
+    import pangenomix.pangenome_analysis as pa
+    for fn in ("estimate_pan_core_size", "fit_heaps_by_iteration", "compute_bernoulli_grid_core_genome",
+               "compute_beta_binomial_core_genome", "ks_montecarlo_bbn", "draw_bbn", "ecdf_from_counts", "betabin_logpmf"):
+        assert callable(getattr(pa, fn)), fn
+    import pangenomix.core_genome as cg
+    assert callable(cg.count_gene_occurence)
