@@ -355,6 +355,12 @@ def test_c5_full_size_spot_parity(engine_mod):
     assert np.all(pan[:, -1] == np.count_nonzero(counts)) and np.all(core[:, -1] == np.count_nonzero(counts == n))
     col_sums = np.bincount(coo.col, minlength=n)
     assert np.array_equal(pan[:, 0], col_sums[perms[:, 0]])
+    # the table's marginals and gene-frequency spectrum at this size (2.0e8 entries through the pinned lanes)
+    row_sum, col_sum, spectrum, first = engine_mod.table_marginals(coo)
+    assert np.array_equal(row_sum, counts) and np.array_equal(col_sum, col_sums)
+    assert np.array_equal(spectrum, np.bincount(counts, minlength=n + 1))
+    seen = np.flatnonzero(spectrum)
+    assert np.array_equal(counts[first[seen]], seen) and np.all(first[seen[1:]] >= 0)
     oracle_build.build()
     threads = os.cpu_count() or 1
     sample = np.r_[0:8, 56:64]
