@@ -40,6 +40,23 @@ KEEP = [
 SCALE = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9, "ns": 1e-6, "us": 1e-3, "ms": 1.0, "s": 1e3}
 
 
+def short_kernel_name(name):
+    """``void pgx::<unnamed>::list_kernel<(int)8, (int)48, (bool)1>(pgx_plan, ...)`` -> ``list_kernel<(int)8, (int)48, (bool)1>``."""
+    import re
+    m = re.search(r"(\w*kernel\w*)", name)
+    if not m:
+        return name.split("(")[0].split("::")[-1]
+    end = m.end()
+    if end < len(name) and name[end] == "<":
+        depth = 0
+        for i in range(end, len(name)):
+            depth += name[i] == "<"
+            depth -= name[i] == ">"
+            if depth == 0:
+                return name[m.start():i + 1]
+    return m.group(1)
+
+
 def main():
     rep, tag, workload, perms = sys.argv[1], sys.argv[2], sys.argv[3], int(sys.argv[4])
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], check=True, capture_output=True, text=True).stdout
@@ -54,7 +71,7 @@ def main():
         w.writerow(["kernel", "metric", "unit", "value"])
         for r in data:
             name = r[idx["Kernel Name"]]
-            short = name.split("::")[-1].split("(")[0]
+            short = short_kernel_name(name)
             vals = {}
             for k in keep:
                 w.writerow([short, k, units[idx[k]], r[idx[k]]])
