@@ -200,6 +200,28 @@ def test_drop_in_host_logic_matches_reference(oracle_device_calls, name):
     _check_against_fixture(_run_drop_in(g), g)
 
 
+def test_count_gene_occurence_host_logic_matches_reference(oracle_device_calls, tmp_path, capsys):
+    """core_genome.count_gene_occurence on the archive to_npz writes, the device counts replaced by numpy's."""
+    from pangenomix_b200 import core_genome
+    from pangenomix_b200.sparse_utils import LightSparseDataFrame
+    g = load_golden("gene_occurence_800x50")
+    shape = tuple(int(v) for v in g["shape"])
+    coo = scipy.sparse.coo_matrix((np.ones(g["row"].shape[0], dtype=np.int64), (g["row"], g["col"])), shape=shape)
+    index, columns = synth.labels_for(*shape)
+    path = os.path.join(str(tmp_path), "t_strain_by_gene.npz")
+    LightSparseDataFrame(np.array(index), np.array(columns), coo).to_npz(path)
+    got = core_genome.count_gene_occurence(path)
+    assert capsys.readouterr().out == "\nCounted gene occurence\n"
+    assert list(got.columns) == [str(c) for c in g["columns"]] and list(got.index) == list(range(len(got)))
+    assert np.array_equal(got["gene_index"].values, g["gene_index"]) and got["gene_index"].dtype == g["gene_index"].dtype
+    assert np.array_equal(got["count"].values, g["count"]) and got["count"].dtype == g["count"].dtype
+    # an archive that is not a to_npz table (no shape / format members): read as the reference reads it
+    plain = os.path.join(str(tmp_path), "plain.npz")
+    np.savez(plain, row=g["row"], col=g["col"])
+    again = core_genome.count_gene_occurence(plain)
+    assert np.array_equal(again.values, got.values)
+
+
 def test_drop_in_helpers_match_oracle():
     from pangenomix_b200 import pangenome_analysis as pa
     x = np.arange(40)
