@@ -10,10 +10,12 @@
 // the image).
 #include <math.h>
 #include <stdint.h>
+#include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
+#include <chrono>
 #include <new>
 #include <numeric>
 #include <vector>
@@ -104,6 +106,15 @@ extern "C" int pgx_host_plan_create(const int32_t *row, const int32_t *col, int6
         Storage *p;
         ~Guard() { delete p; }
     } guard{st};
+    // PGX_PLAN_TRACE=1: seconds per phase on stderr (development aid)
+    const bool trace = getenv("PGX_PLAN_TRACE") != nullptr;
+    auto t_last = std::chrono::steady_clock::now();
+    auto phase = [&](const char *name) {
+        if (!trace) return;
+        const auto now = std::chrono::steady_clock::now();
+        fprintf(stderr, "[pgx plan] %-28s %.3f s\n", name, std::chrono::duration<double>(now - t_last).count());
+        t_last = now;
+    };
     try {
         // ---- canonical gene-major CSR (pangenome_analysis.py:74-75 asks scipy for the genome-major one) ----
         std::vector<int64_t> indptr(static_cast<size_t>(n_genes) + 1, 0);
@@ -120,6 +131,7 @@ extern "C" int pgx_host_plan_create(const int32_t *row, const int32_t *col, int6
                              static_cast<long long>(dups));
         auto m_of = [&](int64_t g) { return indptr[g + 1] - indptr[g]; };
 
+        phase("COO -> CSR");
         // ---- closed forms -------------------------------------------------------------------------------------
         st->w_present.assign(static_cast<size_t>(n), 0);
         st->w_absent.assign(static_cast<size_t>(n), 0);
@@ -140,6 +152,7 @@ extern "C" int pgx_host_plan_create(const int32_t *row, const int32_t *col, int6
             for (int32_t c : missing) ++st->w_absent[c];
         }
 
+        phase("closed forms");
         // ---- bitmap rows: genome-major, bit-sliced, superblocks of rows of similar density, longest walks first ----
         std::vector<int64_t> list_gene;
         for (int64_t g : general) {
@@ -162,6 +175,7 @@ extern "C" int pgx_host_plan_create(const int32_t *row, const int32_t *col, int6
                 return rc;
         }
 
+        phase("bitmap rows");
         // ---- list rows: by chunk count (descending), list kind, length (descending) ... ----
         const long long n_rows = static_cast<long long>(list_gene.size());
         std::vector<uint8_t> use_abs(static_cast<size_t>(n_rows));
@@ -188,6 +202,7 @@ extern "C" int pgx_host_plan_create(const int32_t *row, const int32_t *col, int6
                 n_chunk[i] = (length[i] + CHUNK - 1) / CHUNK;
             }
         }
+        phase("list rows: sort");
         // ... and, inside a (chunk count, kind) class, in the order that balances the bank residues of every
         // wavefront group (PGX_NO_ROW_BALANCE=1 keeps the rows sorted by length)
         const char *no_balance = getenv("PGX_NO_ROW_BALANCE");
@@ -210,6 +225,7 @@ extern "C" int pgx_host_plan_create(const int32_t *row, const int32_t *col, int6
             n_chunk.swap(c2);
             use_abs.swap(a2);
         }
+        phase("list rows: residue balance");
         std::vector<int64_t> ptr(static_cast<size_t>(n_rows) + 1, 0);
         for (long long i = 0; i < n_rows; ++i) ptr[i + 1] = ptr[i] + length[i];
         if (ptr[n_rows] >= (1ll << 31)) return pgx::fail(PGX_ERR_UNSUPPORTED, "list rows too large for int32 offsets");
@@ -221,6 +237,7 @@ extern "C" int pgx_host_plan_create(const int32_t *row, const int32_t *col, int6
             for (int64_t g : list_gene) nnz_list += m_of(g);
         }
 
+        phase("list rows: folded lists");
         // ---- sub-blocks of 32 rows (one lane per row), streamed by a warp in runs of about RUN_LANE_CHUNKS iterations ----
         if (n_rows) {
             std::vector<int64_t> cls_start;
@@ -260,6 +277,7 @@ extern "C" int pgx_host_plan_create(const int32_t *row, const int32_t *col, int6
             if (int rc = pgx_plan_bank_order(flat.data(), ptr.data(), n_rows, block_first.data(), b_nch.data(), b_first_row.data(), b_rows.data(),
                                              n_blocks, n, modulus, COLOUR_MAX_CHUNKS, st->chunks.data(), 0))
                 return rc;
+            phase("list rows: bank order");
             // one task per run; costly runs first: dynamic fetching then ends on cheap ones
             struct Task {
                 int32_t v[4];
@@ -291,6 +309,7 @@ extern "C" int pgx_host_plan_create(const int32_t *row, const int32_t *col, int6
         for (long long i = 0; i < n_rows; ++i) st->row_len[i] = static_cast<int32_t>(length[i]);
         st->row_absent = use_abs;
 
+        phase("tasks, sorted copy");
         pgx_host_plan &v = st->view;
         memset(&v, 0, sizeof(v));
         v.owner = st;
