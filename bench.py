@@ -450,11 +450,16 @@ def run_b200(args, rank, world, local_rank):
             dist.all_reduce(dt, op=dist.ReduceOp.MAX)
         assert np.array_equal(h_out[:64], curves)
         packed = 0 < eng.c_plan.max_colsum <= 65535 and not os.environ.get("PGX_WIDE_BINS")
+        head = int(_native.load().pgx_split_head()) if packed else 0
+        row_bytes = (2 * n + 2 * head) if head > 0 else (4 * n if packed else 8 * n)
         e2e = {"value": perms_all * args.steps / float(dt.item()), "unit": UNIT,
-               "h2d_bytes_per_step": 2 * n * perms_all, "d2h_bytes_per_step": (4 if packed else 8) * n * perms_all,
+               "h2d_bytes_per_step": 2 * n * perms_all, "d2h_bytes_per_step": row_bytes * perms_all,
                "ms_per_step": float(dt.item()) / args.steps * 1e3,
                "path": "pgx_pan_core_curves_host: pinned uint16 permutations in, int32 curves out in host memory, wall clock; "
-                       + ("the device ships the curves' uint16 steps (4N bytes per permutation), host threads rebuild the "
+                       + (("the device ships the curves' steps, the first %d of each curve as uint16 and the rest as uint8 "
+                           "(%d bytes per permutation), host threads rebuild the int32 curves in the caller's buffer inside "
+                           "the timed region" % (head, row_bytes)) if head > 0 else
+                          "the device ships the curves' uint16 steps (4N bytes per permutation), host threads rebuild the "
                           "int32 curves in the caller's buffer inside the timed region" if packed else
                           "int32 curves cross PCIe as they are (a genome holds more than 65,535 genes)"),
                "host_rng_s_per_step_not_included": host_rng_s}

@@ -164,7 +164,8 @@ int pgx_pan_core_curves_f64(const pgx_plan *plan, const uint16_t *d_perms, int64
  * the uploads asynchronous).  The plan stays device-resident.  The call pipelines
  * H2D -> kernels -> D2H -> result over three internal slots in blocks of ``perms_per_block``
  * permutations (0 = choose) and returns when h_curves is complete.  When plan->max_colsum <= 65535 the
- * device ships the curves' STEPS as uint16 (half the bytes of int32 curves, a quarter of float64) into pinned
+ * device ships the curves' STEPS as uint16 (half the bytes of int32 curves, a quarter of float64) -- on tables of
+ * 2,048 genomes or more as uint16 heads + uint8 tails (pgx_expand_split; PGX_SPLIT_HEAD=0 switches that off) -- into pinned
  * staging owned by the library and host threads rebuild the curves straight into h_curves (PGX_COPY_THREADS).
  * Rows of h_perms that are not permutations of 0 .. N-1 make the call fail with PGX_ERR_INVALID.
  * One host-buffer call (this one or pgx_estimate_pan_core) at a time per process. */
@@ -180,6 +181,10 @@ int pgx_pan_core_curves_host(const pgx_plan *plan, const uint16_t *h_perms, int6
  * internal slots; staging is cached for the life of the library.  One call at a time per process. */
 int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_pos, int64_t n_iter,
                           double *h_curves, int64_t perms_per_block);
+
+/* ``head`` of the split row format the host-buffer calls currently use for the table size they last served
+ * (pgx_expand_split; 0 = plain uint16 rows): 2N + 2 head bytes per permutation cross PCIe instead of 4N. */
+int pgx_split_head(void);
 
 /* Launch-shape overrides for experiments (0 = heuristic): permutations per CTA of the list
  * kernel (1, 2, 4 or 8), row splits per permutation batch and threads per CTA. */
@@ -293,6 +298,14 @@ int pgx_inflate_raw(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t d
  * -> curves [n_rows][2N], int32 (out_f64 == 0) or float64.  n_threads 0 = choose. */
 int pgx_expand_deltas(const uint16_t *h_deltas, int64_t n_rows, int32_t n_genomes, void *h_curves,
                       int32_t out_f64, int32_t n_threads);
+
+/* The same for the SPLIT row format the host-buffer calls use on tables of many genomes: a step above 255 only
+ * occurs while the first genomes are added, so the first ``head`` steps of each curve travel as uint16, the rest as
+ * uint8 -- per row [pan head: head x u16][core head: head x u16][pan tail: (N - head) x u8][core tail: (N - head) x u8],
+ * 2N + 2 head bytes instead of 4N (a block with a larger step in a tail is sent again as uint16 and ``head`` doubled
+ * for the blocks after it).  1 <= head <= N. */
+int pgx_expand_split(const uint8_t *h_rows, int64_t n_rows, int32_t n_genomes, int32_t head, void *h_curves,
+                     int32_t out_f64, int32_t n_threads);
 
 /* numpy legacy RandomState stream (host): ``count`` consecutive
  * ``a = np.arange(n); np.random.shuffle(a)`` results as uint16 rows, continuing from the

@@ -23,7 +23,7 @@ EXPORTS = (
     "pgx_plan_missing_genome", "pgx_plan_all_equal_u64", "pgx_plan_balance_rows", "pgx_inflate_raw",
     "pgx_expand_deltas", "pgx_host_plan_create", "pgx_host_plan_destroy", "pgx_plan_create", "pgx_plan_upload",
     "pgx_plan_destroy", "pgx_set_trace", "pgx_legacy_random_raw", "pgx_coo_marginals", "pgx_frequency_spectrum",
-    "pgx_coo_marginals_host", "pgx_ks_scratch_bytes", "pgx_ks_montecarlo", "pgx_ks_montecarlo_host",
+    "pgx_coo_marginals_host", "pgx_ks_scratch_bytes", "pgx_ks_montecarlo", "pgx_ks_montecarlo_host", "pgx_expand_split", "pgx_split_head",
 )
 
 
@@ -160,6 +160,10 @@ def load():
     lib.pgx_plan_destroy.argtypes = [plan_p]
     lib.pgx_expand_deltas.restype = ctypes.c_int
     lib.pgx_expand_deltas.argtypes = [vp, i64, i32, vp, i32, i32]
+    lib.pgx_split_head.restype = ctypes.c_int
+    lib.pgx_split_head.argtypes = []
+    lib.pgx_expand_split.restype = ctypes.c_int
+    lib.pgx_expand_split.argtypes = [vp, i64, i32, i32, vp, i32, i32]
     lib.pgx_estimate_pan_core.restype = ctypes.c_int
     lib.pgx_estimate_pan_core.argtypes = [plan_p, vp, ctypes.POINTER(i32), i64, vp, i64]
     lib.pgx_heaps_scratch_bytes.restype = ctypes.c_size_t

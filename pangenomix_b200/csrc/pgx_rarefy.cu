@@ -59,6 +59,7 @@
 namespace pgx {
 
 void expand_delta_rows(const uint16_t *deltas, long long r0, long long r1, long long n, void *out, bool out_f64);
+void expand_split_rows(const uint8_t *rows, long long r0, long long r1, long long n, long long head, void *out, bool out_f64);
 
 namespace {
 
@@ -1255,6 +1256,46 @@ int run_curves(const pgx_plan *plan, const uint16_t *d_perms, long long n_perm, 
 // ---------------------------------------------------------------------------------------------
 constexpr int SLOTS = 3;
 
+// Packed histogram rows -> the SPLIT transfer format (pgx_expand.cpp): per row [pan head: head x u16][core head: head x
+// u16][pan tail: (N - head) x u8][core tail: (N - head) x u8].  A step above 255 only occurs while the first genomes are
+// added (C4: none after position 123), so the tails fit a byte; a row that breaks the rule raises ``overflow`` and its
+// block travels again as uint16.  One CTA per row; entry e of the row (pan bins, then core bins) is half (e & 1) of
+// word e >> 1.
+__global__ void __launch_bounds__(256)
+split_steps_kernel(const uint32_t *__restrict__ hist, const long long hist_stride, const int n, const int head,
+                   uint8_t *__restrict__ out, const long long out_stride, int *__restrict__ overflow)
+{
+    const uint32_t *row = hist + static_cast<long long>(blockIdx.x) * hist_stride;
+    uint8_t *dst = out + static_cast<long long>(blockIdx.x) * out_stride;
+    uint16_t *head16 = reinterpret_cast<uint16_t *>(dst);                   // [2][head]
+    uint8_t *tail8 = dst + 4ll * head;                                      // [2][n - head]
+    int over = 0;
+    for (int w = threadIdx.x; w < n; w += blockDim.x) {
+        const uint32_t v = row[w];
+#pragma unroll
+        for (int h = 0; h < 2; ++h) {
+            const int e = 2 * w + h;
+            const uint32_t x = h ? v >> 16 : v & 0xffffu;
+            const int half = e >= n ? 1 : 0, pos = e - half * n;
+            if (pos < head) {
+                head16[half * head + pos] = static_cast<uint16_t>(x);
+            } else {
+                tail8[static_cast<long long>(half) * (n - head) + (pos - head)] = static_cast<uint8_t>(min(x, 255u));
+                over |= x > 255u;
+            }
+        }
+    }
+    if (__syncthreads_or(over) && threadIdx.x == 0) *overflow = 1;         // host-mapped flag: any writer writes 1
+}
+
+// First guess of ``head`` (PGX_SPLIT_HEAD; 0 = never split) -- doubled whenever a block overflows; the split format
+// is used while 4 head <= N.
+int split_head_initial()
+{
+    const char *env = getenv("PGX_SPLIT_HEAD");
+    return env ? std::max(0, atoi(env)) : 512;
+}
+
 struct Slot {
     cudaStream_t stream = nullptr;
     cudaEvent_t done = nullptr;
@@ -1265,6 +1306,9 @@ struct Slot {
     uint32_t *d_hist = nullptr;       // packed mode: [block][N] words; wide mode: int32 [block][2N]
     double *d_f64 = nullptr;          // wide mode, float64 output
     uint16_t *h_rows = nullptr;       // pinned staging: packed rows (uint16 [block][2N]); wide mode: curves as they are
+    uint8_t *d_split = nullptr;       // packed mode: the block's rows in the split format
+    int *h_overflow = nullptr;        // host-mapped: a tail step of the block did not fit a byte
+    int head = 0;                     // split format of the block in flight (0: plain uint16 rows)
 };
 
 struct Pipe {
@@ -1272,6 +1316,7 @@ struct Pipe {
     long long block = 0, n = 0;
     bool packed = false, f64 = false, rng = false;
     int *bad_rows = nullptr;          // host-mapped counter of rows that are not permutations
+    std::atomic<int> split_head{0};   // current ``head`` of the split format for this table size (0: plain uint16 rows)
     Slot slot[SLOTS];
 };
 
@@ -1284,6 +1329,8 @@ void release(Pipe &b)
         if (s.d_rank) cudaFree(s.d_rank);
         if (s.d_hist) cudaFree(s.d_hist);
         if (s.d_f64) cudaFree(s.d_f64);
+        if (s.d_split) cudaFree(s.d_split);
+        if (s.h_overflow) cudaFreeHost(s.h_overflow);
         if (s.done) cudaEventDestroy(s.done);
         if (s.stream) cudaStreamDestroy(s.stream);
         if (s.aux.stream) cudaStreamDestroy(s.aux.stream);
@@ -1316,6 +1363,9 @@ int acquire(Pipe &b, int device, long long block, long long n, bool packed, bool
             PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_rank), sizeof(uint16_t) * block * n));
             PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_hist), sizeof(uint32_t) * block * n));
             PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s.h_rows), sizeof(uint16_t) * block * 2 * n, cudaHostAllocDefault));
+            PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_split), sizeof(uint16_t) * block * 2 * n));      // never more than the plain rows
+            PGX_CUDA(cudaHostAlloc(reinterpret_cast<void **>(&s.h_overflow), sizeof(int), cudaHostAllocMapped));
+            *s.h_overflow = 0;
         } else {
             PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_hist), sizeof(int32_t) * block * 2 * n));
             if (f64) PGX_CUDA(cudaMalloc(reinterpret_cast<void **>(&s.d_f64), sizeof(double) * block * 2 * n));
@@ -1329,6 +1379,8 @@ int acquire(Pipe &b, int device, long long block, long long n, bool packed, bool
     b.packed = packed;
     b.f64 = f64;
     b.rng = rng;
+    const int head = split_head_initial();
+    b.split_head.store(packed && head > 0 && 4ll * head <= n ? head : 0);
     return PGX_OK;
 }
 
@@ -1401,8 +1453,9 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
     // counters: on the virtualised hosts this runs on, waking a sleeping thread costs 0.2-0.5 ms.
     std::atomic<long long> issued{0}, retired{0};
     std::atomic<int> failed{0};
-    std::vector<std::atomic<int>> parts_done(static_cast<size_t>(n_blocks));
+    std::vector<std::atomic<int>> parts_done(static_cast<size_t>(n_blocks)), refetch(static_cast<size_t>(n_blocks));
     for (auto &c : parts_done) c.store(0, std::memory_order_relaxed);
+    for (auto &c : refetch) c.store(0, std::memory_order_relaxed);
     int movers = std::max(1, std::min(rng ? 6 : 12, static_cast<int>(std::thread::hardware_concurrency()) - (rng ? 3 : 2)));
     if (const char *env = getenv("PGX_COPY_THREADS")) movers = std::max(1, std::min(32, atoi(env)));
     movers = static_cast<int>(std::max<long long>(1, std::min<long long>(movers, max_block * n / 32768)));
@@ -1422,7 +1475,31 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
             const long long p0 = first_perm[k], cnt = first_perm[k + 1] - p0;
             const long long r0 = cnt * t / movers, r1 = cnt * (t + 1) / movers;
             char *dst = static_cast<char *>(h_curves) + out_elem * 2 * n * p0;
-            if (packed) {
+            if (packed && s.head > 0 && *s.h_overflow) {
+                // a tail step above 255: the block's plain uint16 rows are still in the slot; the first mover to get
+                // here fetches them, the others wait, and later blocks get a longer head
+                int expect = 0;
+                std::atomic<int> &state = refetch[static_cast<size_t>(k)];
+                if (state.compare_exchange_strong(expect, 1, std::memory_order_acq_rel)) {
+                    int next = 2 * s.head;
+                    if (4ll * next > n) next = 0;
+                    int seen = buf.split_head.load();
+                    while (seen == s.head && !buf.split_head.compare_exchange_weak(seen, next)) {}
+                    const bool ok = cudaMemcpyAsync(s.h_rows, s.d_hist, sizeof(uint16_t) * cnt * 2 * n, cudaMemcpyDeviceToHost, s.stream) == cudaSuccess &&
+                                    cudaStreamSynchronize(s.stream) == cudaSuccess;
+                    if (trace) fprintf(stderr, "[pgx trace] block %lld: head %d overflowed, fetched as uint16 (%.2f ms)\n", k, s.head, since());
+                    state.store(ok ? 2 : 3, std::memory_order_release);
+                }
+                int st;
+                while ((st = state.load(std::memory_order_acquire)) < 2) std::this_thread::yield();
+                if (st == 3) {
+                    failed.store(1);
+                    return;
+                }
+                expand_delta_rows(s.h_rows, r0, r1, n, dst, out_f64);
+            } else if (packed && s.head > 0) {
+                expand_split_rows(reinterpret_cast<const uint8_t *>(s.h_rows), r0, r1, n, s.head, dst, out_f64);
+            } else if (packed) {
                 expand_delta_rows(s.h_rows, r0, r1, n, dst, out_f64);
             } else {
                 const size_t row = out_elem * 2 * n;
@@ -1455,9 +1532,26 @@ int host_pipeline(const pgx_plan *plan, const uint16_t *h_perms, uint32_t *mt_ke
         if (!rc && packed) {
             Work work{s.d_hist, n, s.d_rank, n};
             rc = run_rows<true>(plan, s.d_perm, cnt, work, d_bad_rows, s.stream, &s.aux, nullptr);
-            if (!rc && cudaMemcpyAsync(s.h_rows, s.d_hist, sizeof(uint16_t) * cnt * 2 * n, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
+            s.head = buf.split_head.load();
+            if (!rc && s.head > 0) {
+                // uint16 heads + uint8 tails: 2N + 2 head bytes per row over PCIe and through the host's memory
+                int *d_overflow = nullptr;
+                *s.h_overflow = 0;
+                if (cudaHostGetDevicePointer(reinterpret_cast<void **>(&d_overflow), s.h_overflow, 0) != cudaSuccess)
+                    rc = fail(PGX_ERR_CUDA, "cudaHostGetDevicePointer failed: %s", cudaGetErrorString(cudaGetLastError()));
+                const long long row_bytes = 2 * n + 2ll * s.head;
+                if (!rc) {
+                    split_steps_kernel<<<static_cast<unsigned>(cnt), 256, 0, s.stream>>>(s.d_hist, n, static_cast<int>(n), s.head, s.d_split,
+                                                                                         row_bytes, d_overflow);
+                    if (cudaGetLastError() != cudaSuccess) rc = fail(PGX_ERR_CUDA, "launch of split_steps_kernel failed");
+                    else g_launches.fetch_add(1, std::memory_order_relaxed);
+                }
+                if (!rc && cudaMemcpyAsync(s.h_rows, s.d_split, static_cast<size_t>(row_bytes) * cnt, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
+                    rc = fail(PGX_ERR_CUDA, "D2H copy of the curve steps failed: %s", cudaGetErrorString(cudaGetLastError()));
+            } else if (!rc && cudaMemcpyAsync(s.h_rows, s.d_hist, sizeof(uint16_t) * cnt * 2 * n, cudaMemcpyDeviceToHost, s.stream) != cudaSuccess)
                 rc = fail(PGX_ERR_CUDA, "D2H copy of the curve steps failed: %s", cudaGetErrorString(cudaGetLastError()));
         } else if (!rc) {
+            s.head = 0;
             rc = out_f64 ? run_curves<double>(plan, s.d_perm, cnt, reinterpret_cast<int32_t *>(s.d_hist), s.d_f64, s.stream, &s.aux, d_bad_rows)
                          : run_curves<int32_t>(plan, s.d_perm, cnt, reinterpret_cast<int32_t *>(s.d_hist),
                                                reinterpret_cast<int32_t *>(s.d_hist), s.stream, &s.aux, d_bad_rows);
@@ -1525,6 +1619,11 @@ int pgx_estimate_pan_core(const pgx_plan *plan, uint32_t *mt_key, int32_t *mt_po
     if (!mt_key || !mt_pos || (!h_curves && n_iter > 0)) return pgx::fail(PGX_ERR_INVALID, "null pointer");
     if (n_iter == 0) return PGX_OK;
     return pgx::host_pipeline(plan, nullptr, mt_key, mt_pos, n_iter, h_curves, true, perms_per_block);
+}
+
+int pgx_split_head(void)
+{
+    return pgx::g_pipe.split_head.load();
 }
 
 int pgx_profile_enable(int32_t on)

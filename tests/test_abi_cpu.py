@@ -233,3 +233,34 @@ def test_c_host_links_only_the_library_and_plans_a_table(tmp_path):
     assert "host ok" in out and "bitmap rows" in out
     needed = subprocess.run(["ldd", exe], check=True, capture_output=True, text=True).stdout
     assert "libpgx_b200.so" in needed and "python" not in needed.lower() and "torch" not in needed.lower()
+
+
+@pytest.mark.parametrize("n, head, rows", [(2048, 512, 37), (3001, 7, 11), (5, 5, 3), (9, 1, 4), (40, 39, 5), (10000, 512, 20)])
+def test_split_rows_expand_to_the_curves(n, head, rows):
+    """pgx_expand_split: uint16 heads + uint8 tails of the curves' steps -> int32 / float64 curves (the host half of
+    the host-buffer calls on tables of many genomes), any thread count, aligned or not."""
+    lib = _native.load()
+    rng = np.random.RandomState(n + head)
+    pan = rng.randint(0, 200, size=(rows, n))
+    pan[:, :head] = rng.randint(0, 5000, size=(rows, head))
+    core = rng.randint(0, 3, size=(rows, n))
+    core[:, :head] = rng.randint(0, 300, size=(rows, head))
+    core[:, 0] = 60000
+    want = np.hstack([np.cumsum(pan, axis=1),
+                      core[:, :1] - np.hstack([np.zeros((rows, 1), dtype=np.int64), np.cumsum(core[:, 1:], axis=1)])])
+    packed = np.zeros((rows, 2 * n + 2 * head), dtype=np.uint8)
+    packed[:, :2 * head].view(np.uint16)[:, :] = pan[:, :head]
+    packed[:, 2 * head:4 * head].view(np.uint16)[:, :] = core[:, :head]
+    packed[:, 4 * head:4 * head + (n - head)] = pan[:, head:]
+    packed[:, 4 * head + (n - head):] = core[:, head:]
+    for f64 in (0, 1):
+        for threads in (1, 3):
+            out = np.full((rows, 2 * n), -7, dtype=np.float64 if f64 else np.int32)
+            assert lib.pgx_expand_split(packed.ctypes.data, rows, n, head, out.ctypes.data, f64, threads) == 0
+            assert np.array_equal(out.astype(np.int64), want)
+    buf = np.zeros(rows * 2 * n + 3, dtype=np.int32)
+    unaligned = buf[1:1 + rows * 2 * n]
+    assert lib.pgx_expand_split(packed.ctypes.data, rows, n, head, unaligned.ctypes.data, 0, 2) == 0
+    assert np.array_equal(unaligned.reshape(rows, 2 * n).astype(np.int64), want)
+    assert lib.pgx_expand_split(packed.ctypes.data, rows, n, 0, buf.ctypes.data, 0, 1) == 1          # head out of range
+    assert lib.pgx_expand_split(packed.ctypes.data, rows, n, n + 1, buf.ctypes.data, 0, 1) == 1

@@ -393,6 +393,56 @@ def test_genomes_above_65535_genes_use_int32_bins(engine_mod):
     assert np.array_equal(eng.estimate(21), want.astype(np.float64))
 
 
+def _many_genomes_table(n, seed):
+    from pangenomix_b200 import synth
+    return synth.bernoulli_matrix(20000, n, 3000, seed=seed).tocoo()
+
+
+def test_split_transfer_of_tables_with_many_genomes(engine_mod):
+    """Tables of 2,048 genomes or more: the host-buffer calls ship uint16 heads + uint8 tails of the curves' steps
+    (split_steps_kernel, pgx_expand_split).  Same curves as the oracle's for int32 and float64 results, ragged blocks
+    and the RNG-fed call."""
+    from pangenomix_b200 import _native
+    n = 2304
+    coo = _many_genomes_table(n, seed=3)
+    eng = engine_mod.PanCoreEngine(coo)
+    perms = draw_perms(5, n, 45).astype(np.uint16)
+    want = _oracle_curves(coo, perms)
+    for block in (0, 7, 16):
+        assert np.array_equal(eng.curves_host(perms, perms_per_block=block), want)
+    assert int(_native.load().pgx_split_head()) == 512
+    assert np.array_equal(eng.curves_host(perms, out_f64=True, perms_per_block=11), want.astype(np.float64))
+    np.random.seed(5)
+    assert np.array_equal(eng.estimate(45), want.astype(np.float64))
+
+
+def test_split_transfer_recovers_from_a_head_that_is_too_short(engine_mod):
+    """PGX_SPLIT_HEAD=4 (read when the staging is set up for a new table size): the first genomes add thousands of
+    genes each, the 4-entry heads overflow, the blocks in flight travel again as uint16 and the head doubles until the
+    tails fit -- with the same curves throughout."""
+    import os
+    from pangenomix_b200 import _native
+    n = 2112                                             # a size no other test uses: the staging is set up anew
+    coo = _many_genomes_table(n, seed=4)
+    eng = engine_mod.PanCoreEngine(coo)
+    perms = draw_perms(6, n, 90).astype(np.uint16)
+    want = _oracle_curves(coo, perms)
+    old = os.environ.get("PGX_SPLIT_HEAD")
+    os.environ["PGX_SPLIT_HEAD"] = "4"
+    try:
+        got = eng.curves_host(perms, perms_per_block=6)
+        grown = int(_native.load().pgx_split_head())
+        assert np.array_equal(got, want)
+        assert grown > 4 and grown % 4 == 0
+        assert np.array_equal(eng.curves_host(perms, out_f64=True, perms_per_block=6), want.astype(np.float64))
+        assert int(_native.load().pgx_split_head()) >= grown
+    finally:
+        if old is None:
+            del os.environ["PGX_SPLIT_HEAD"]
+        else:
+            os.environ["PGX_SPLIT_HEAD"] = old
+
+
 def test_c_host_program_end_to_end(engine_mod, tmp_path):
     """tests/c/abi_host.c --gpu: plan, upload, rarefy and check 21 genome orders from plain C through the C ABI alone
     (pgx_host_plan_create, pgx_plan_upload, pgx_pan_core_curves_host, pgx_plan_create, pgx_plan_destroy)."""
