@@ -264,3 +264,44 @@ def test_split_rows_expand_to_the_curves(n, head, rows):
     assert np.array_equal(unaligned.reshape(rows, 2 * n).astype(np.int64), want)
     assert lib.pgx_expand_split(packed.ctypes.data, rows, n, 0, buf.ctypes.data, 0, 1) == 1          # head out of range
     assert lib.pgx_expand_split(packed.ctypes.data, rows, n, n + 1, buf.ctypes.data, 0, 1) == 1
+
+
+def _split_rows_from_hist(words, n, head):
+    """numpy restatement of split_steps_kernel (csrc/pgx_rarefy.cu): packed histogram rows -- entry e of a row (pan bins,
+    then core bins) in half (e & 1) of 32-bit word e >> 1 -- to the split transfer format, plus the overflow flag."""
+    rows = words.shape[0]
+    entries = words.view(np.uint16).reshape(rows, 2 * n)             # little-endian: the low half is the even entry
+    out = np.zeros((rows, 2 * n + 2 * head), dtype=np.uint8)
+    heads = out[:, :4 * head].view(np.uint16)
+    heads[:, :head] = entries[:, :head]
+    heads[:, head:] = entries[:, n:n + head]
+    out[:, 4 * head:4 * head + (n - head)] = np.minimum(entries[:, head:n], 255)
+    out[:, 4 * head + (n - head):] = np.minimum(entries[:, n + head:], 255)
+    overflow = bool((entries[:, head:n] > 255).any() or (entries[:, n + head:] > 255).any())
+    return out, overflow
+
+
+@pytest.mark.parametrize("n, head", [(2048, 512), (2049, 512), (2051, 1), (4097, 1024), (7, 3), (6, 6)])
+def test_split_format_agrees_with_the_uint16_rows(n, head):
+    """The two transfer formats of the host-buffer calls decode to the same curves: a packed histogram row read as 2N
+    uint16 steps (pgx_expand_deltas) and the same row in the split format (pgx_expand_split), odd N included (the
+    pan / core boundary then falls inside a word)."""
+    lib = _native.load()
+    rng = np.random.RandomState(n * 31 + head)
+    rows = 9
+    steps = rng.randint(0, 256, size=(rows, 2 * n)).astype(np.uint16)
+    steps[:, :head] = rng.randint(0, 60000, size=(rows, head))        # large steps inside the heads only
+    steps[:, n:n + head] = rng.randint(0, 300, size=(rows, head))
+    steps[:, n] = 65535
+    words = np.ascontiguousarray(steps).view(np.uint32).reshape(rows, n)
+    split, overflow = _split_rows_from_hist(words, n, head)
+    assert not overflow
+    a = np.empty((rows, 2 * n), dtype=np.int32)
+    b = np.empty((rows, 2 * n), dtype=np.int32)
+    assert lib.pgx_expand_deltas(steps.ctypes.data, rows, n, a.ctypes.data, 0, 2) == 0
+    assert lib.pgx_expand_split(split.ctypes.data, rows, n, head, b.ctypes.data, 0, 2) == 0
+    assert np.array_equal(a, b)
+    if head < n:
+        steps[3, n - 1] = 256                                         # a tail step that does not fit a byte
+        words = np.ascontiguousarray(steps).view(np.uint32).reshape(rows, n)
+        assert _split_rows_from_hist(words, n, head)[1]
