@@ -36,7 +36,7 @@
 extern "C" {
 #endif
 
-#define PGX_VERSION 310
+#define PGX_VERSION 320
 
 enum {
     PGX_OK = 0,
