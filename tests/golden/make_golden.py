@@ -6,6 +6,7 @@ Run in the build container only (the reference does not exist on the GPU box):
     python tests/golden/make_golden.py            # the round-1 fixtures
     python tests/golden/make_golden.py --big      # the full-size fixtures of round 2 (C2, C4, C3; ~3 min)
     python tests/golden/make_golden.py --betabin  # beta-binomial core estimate, Monte-Carlo KS, gene occurrence
+    python tests/golden/make_golden.py --c5       # one permutation of config C5 at full size (tens of minutes)
 
 The reference has no tests or golden vectors of its own, so
 these fixtures -- outputs of the unmodified reference functions under a fixed
@@ -253,7 +254,25 @@ def betabin_cases(manifest):
     print("wrote gene_occurence_800x50", occ.shape, occ.dtypes.to_dict())
 
 
+def c5_case(manifest):
+    """Config C5 at full size (2,000,000 alleles x 50,000 genomes, nnz 2.0e8): ONE permutation through the live
+    reference (about 50,000 dense passes over 2 M counters: tens of minutes on the build host)."""
+    import time
+    c5 = synth.config_matrix("c5")
+    t = time.time()
+    save_curve_case("c5_2000000x50000", c5, 12345, 1, store_matrix=False, heaps=False)
+    manifest["c5_2000000x50000_reference_seconds_per_permutation"] = time.time() - t
+
+
 def main():
+    if "--c5" in sys.argv:
+        path = os.path.join(HERE, "MANIFEST.json")
+        with open(path) as f:
+            manifest = json.load(f)
+        c5_case(manifest)
+        with open(path, "w") as f:
+            json.dump(manifest, f, indent=1, sort_keys=True)
+        return
     if "--betabin" in sys.argv:
         path = os.path.join(HERE, "MANIFEST.json")
         with open(path) as f:

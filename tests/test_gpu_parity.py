@@ -368,6 +368,12 @@ def test_c5_full_size_spot_parity(engine_mod):
     del coo
     ref_pan, ref_core = cport.curves_direct(gm, perms[sample].astype(np.int32), n_threads=min(threads, 16))
     assert np.array_equal(curves[sample], np.hstack([ref_pan, ref_core]).astype(np.int32))
+    # ... and the first curve against the live reference's own (tests/golden/make_golden.py --c5; the same seed)
+    fixture = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "c5_2000000x50000.npz")
+    if os.path.exists(fixture):
+        g5 = np.load(fixture)
+        assert int(g5["seed"]) == 12345 and tuple(int(v) for v in g5["shape"]) == (g, n)
+        assert np.array_equal(curves[0], g5["curves"][0])
     # the reference-facing call on the same table: float64, the same rows
     np.random.seed(12345)
     assert np.array_equal(eng.estimate(8), curves[:8].astype(np.float64))

@@ -148,3 +148,18 @@ def test_bernoulli_ll_grad_at_c3_size():
         np.testing.assert_allclose(oracle.bernoulli_grad(x, pq[:4000], pq[4000:]), g["grad_" + tag], rtol=1e-12)
     assert float(g["ll_init"]) == float(g["fit_initial"][0])
     np.testing.assert_allclose(g["ll_opt"], -float(g["fit_fun"]), rtol=1e-15)
+
+
+@pytest.mark.skipif(__import__("os").environ.get("PGX_TEST_C5") != "1",
+                    reason="config C5 at full size: 3 GB of table and a minute of C port per permutation (PGX_TEST_C5=1)")
+def test_c_port_matches_reference_on_c5():
+    """The live reference's own curve of ONE permutation of config C5 at full size (2,000,000 x 50,000; the reference
+    needs tens of minutes for it, tests/golden/make_golden.py --c5) against the oracle's C port -- the checker of the
+    full-size GPU test, which also compares the GPU curve with this fixture."""
+    import os
+    from oracle import cport
+    g = load_golden("c5_2000000x50000")
+    coo = golden_matrix("c5_2000000x50000", g)
+    perms = draw_perms(int(g["seed"]), coo.shape[1], 1)
+    pan, core = cport.curves_direct(coo, perms.astype(np.int32), n_threads=1)
+    assert np.array_equal(np.hstack([pan, core]).astype(np.int32), g["curves"])
