@@ -7,6 +7,7 @@ Run in the build container only (the reference does not exist on the GPU box):
     python tests/golden/make_golden.py --big      # the full-size fixtures of round 2 (C2, C4, C3; ~3 min)
     python tests/golden/make_golden.py --betabin  # beta-binomial core estimate, Monte-Carlo KS, gene occurrence
     python tests/golden/make_golden.py --c5       # one permutation of config C5 at full size (tens of minutes)
+    python tests/golden/make_golden.py --c3-whole # the reference's Bernoulli fit on the whole table, 40,000 x 400 (minutes)
 
 The reference has no tests or golden vectors of its own, so
 these fixtures -- outputs of the unmodified reference functions under a fixed
@@ -254,6 +255,34 @@ def betabin_cases(manifest):
     print("wrote gene_occurence_800x50", occ.shape, occ.dtypes.to_dict())
 
 
+def bernoulli_whole_table_case(manifest):
+    """Config C3 on the whole table (40,000 genes x 400 genomes, README.md:199-211): the reference's full L-BFGS-B fit
+    (minutes), its LL and gradient at the start point and at its optimum."""
+    import time
+    x, _, _ = synth.bernoulli_grid_matrix(40000, 400, seed=3)
+    n_genes, n_genomes = x.shape
+    index, columns = synth.labels_for(n_genes, n_genomes)
+    dense = pd.DataFrame(x, index=index, columns=columns)
+    t = time.time()
+    df_opt, res = quiet(ref_pa.compute_bernoulli_grid_core_genome, dense)
+    fit_seconds = time.time() - t
+    ll = ref_pa.__dict__["__bernoulli_grid_loglikelihood__"]
+    grad = ref_pa.__dict__["__bernoulli_grid_loglikelihood_gradient__"]
+    init = df_opt["initial"].values[1:]
+    opt = df_opt["optimum"].values[1:]
+    np.savez_compressed(
+        os.path.join(HERE, "bernoulli_c3_40000x400.npz"),
+        shape=np.asarray(x.shape, dtype=np.int64), x_digest=np.array(hashlib.sha256(x.astype(np.uint8).tobytes()).hexdigest()),
+        fit_ll_initial=np.float64(df_opt["initial"].values[0]), fit_x=res.x, fit_fun=np.float64(res.fun),
+        fit_nit=np.int64(res.nit), fit_nfev=np.int64(res.nfev), fit_message=np.array(str(res.message)),
+        fit_seconds=np.float64(fit_seconds),
+        ll_init=np.float64(ll(x, init[:n_genes], init[n_genes:])), grad_init=grad(x, init[:n_genes], init[n_genes:]),
+        ll_opt=np.float64(ll(x, opt[:n_genes], opt[n_genes:])), grad_opt=grad(x, opt[:n_genes], opt[n_genes:]))
+    manifest["bernoulli_c3_40000x400_reference_fit_seconds"] = fit_seconds
+    print("wrote bernoulli_c3_40000x400: init LL", df_opt["initial"].values[0], "opt LL", -res.fun, "nit", res.nit,
+          "nfev", res.nfev, "%.1fs" % fit_seconds)
+
+
 def c5_case(manifest):
     """Config C5 at full size (2,000,000 alleles x 50,000 genomes, nnz 2.0e8): ONE permutation through the live
     reference (about 50,000 dense passes over 2 M counters: tens of minutes on the build host)."""
@@ -265,6 +294,14 @@ def c5_case(manifest):
 
 
 def main():
+    if "--c3-whole" in sys.argv:
+        path = os.path.join(HERE, "MANIFEST.json")
+        with open(path) as f:
+            manifest = json.load(f)
+        bernoulli_whole_table_case(manifest)
+        with open(path, "w") as f:
+            json.dump(manifest, f, indent=1, sort_keys=True)
+        return
     if "--c5" in sys.argv:
         path = os.path.join(HERE, "MANIFEST.json")
         with open(path) as f:

@@ -163,3 +163,19 @@ def test_c_port_matches_reference_on_c5():
     perms = draw_perms(int(g["seed"]), coo.shape[1], 1)
     pan, core = cport.curves_direct(coo, perms.astype(np.int32), n_threads=1)
     assert np.array_equal(np.hstack([pan, core]).astype(np.int32), g["curves"])
+
+
+def test_bernoulli_ll_grad_on_the_whole_table():
+    """The oracle at the whole-table size of config C3 (40,000 x 400) against the live reference's numbers at its start
+    point and at its optimum (make_golden.py --c3-whole)."""
+    import hashlib
+    from pangenomix_b200 import synth
+    g = load_golden("bernoulli_c3_40000x400")
+    x, _, _ = synth.bernoulli_grid_matrix(40000, 400, seed=3)
+    assert hashlib.sha256(x.astype(np.uint8).tobytes()).hexdigest() == str(g["x_digest"])
+    init = np.clip(np.concatenate((x.sum(axis=1) / 400.0, 0.9999 * np.ones(400))), 0.8, 0.99999999)
+    for tag, pq in (("init", init), ("opt", g["fit_x"])):
+        np.testing.assert_allclose(oracle.bernoulli_ll(x, pq[:40000], pq[40000:]), g["ll_" + tag], rtol=1e-13)
+        np.testing.assert_allclose(oracle.bernoulli_grad(x, pq[:40000], pq[40000:]), g["grad_" + tag], rtol=1e-12,
+                                   atol=1e-12 * np.abs(g["grad_" + tag]).max())
+    assert float(g["fit_ll_initial"]) == float(g["ll_init"])
