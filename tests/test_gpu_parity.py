@@ -50,7 +50,7 @@ def test_curves_match_reference_fixtures(engine_mod, name):
 @pytest.mark.parametrize("name", BIG_CURVE_CASES)
 def test_curves_match_live_reference_at_full_size(engine_mod, name):
     """Configs C2 and C4 at BASELINE.json's full size against curves the LIVE reference computed for the same table
-    and seed (tests/golden/make_golden.py --big): 64 permutations of C2, 4 of C4; both C-ABI paths."""
+    and seed (tests/golden/make_golden.py --big): 64 permutations of C2, 16 of C4; both C-ABI paths."""
     import torch
     g = load_golden(name)
     coo = golden_matrix(name, g)

@@ -46,7 +46,7 @@ def test_c_port_matches_reference(name):
 def test_minrank_matches_reference_at_full_size(name):
     g = load_golden(name)
     coo = golden_matrix(name, g)
-    num_iter = min(int(g["num_iter"]), 8)
+    num_iter = min(int(g["num_iter"]), 4)
     perms = draw_perms(int(g["seed"]), coo.shape[1], num_iter)
     pan, core = oracle.pan_core_curves_minrank(coo, perms)
     assert np.array_equal(np.hstack([pan, core]), g["curves"][:num_iter].astype(np.float64))
