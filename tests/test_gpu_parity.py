@@ -50,7 +50,7 @@ def test_curves_match_reference_fixtures(engine_mod, name):
 @pytest.mark.parametrize("name", BIG_CURVE_CASES)
 def test_curves_match_live_reference_at_full_size(engine_mod, name):
     """Configs C2 and C4 at BASELINE.json's full size against curves the LIVE reference computed for the same table
-    and seed (tests/golden/make_golden.py --big): 64 permutations of C2, 16 of C4; both C-ABI paths."""
+    and seed (tests/golden/make_golden.py --big): all 1,000 permutations of C2, 16 of C4; both C-ABI paths."""
     import torch
     g = load_golden(name)
     coo = golden_matrix(name, g)
@@ -63,7 +63,17 @@ def test_curves_match_live_reference_at_full_size(engine_mod, name):
     assert np.array_equal(eng.curves_host(perms, out_f64=True), want.astype(np.float64))
     assert np.array_equal(eng.curves_device(torch.from_numpy(perms.view(np.int16)).cuda()).cpu().numpy(), want)
     np.random.seed(int(g["seed"]))
-    assert np.array_equal(eng.estimate(num_iter), want.astype(np.float64))
+    table = eng.estimate(num_iter)
+    assert np.array_equal(table, want.astype(np.float64))
+    if name == "c2_40000x400":
+        # config C2 as BASELINE.json states it: 1,000 permutations + the Heaps fit on their mean
+        from pangenomix_b200 import pangenome_analysis as pa, plot
+        n = coo.shape[1]
+        assert num_iter == 1000
+        df = pd.DataFrame(table, columns=["Pan%d" % (i + 1) for i in range(n)] + ["Core%d" % (i + 1) for i in range(n)])
+        mean = plot.calculate_mean(df)
+        assert np.array_equal(mean.values[0], g["mean"])
+        np.testing.assert_allclose(pa.fit_heaps_by_iteration(mean).values[0], g["heaps_mean"], rtol=1e-9)
 
 
 @pytest.mark.parametrize("name", ["kat_6x5", "synth_800x50_s0", "c1_8000x50", "c2slice_4000x400"])

@@ -179,3 +179,19 @@ def test_bernoulli_ll_grad_on_the_whole_table():
         np.testing.assert_allclose(oracle.bernoulli_grad(x, pq[:40000], pq[40000:]), g["grad_" + tag], rtol=1e-12,
                                    atol=1e-12 * np.abs(g["grad_" + tag]).max())
     assert float(g["fit_ll_initial"]) == float(g["ll_init"])
+
+
+def test_config_c2_mean_and_heaps_fit_of_the_reference():
+    """Config C2 in full (1,000 permutations + the Heaps fit on their mean, BASELINE.json): the host half of the
+    drop-in (plot.calculate_mean, fit_heaps_by_iteration) applied to the live reference's curves gives the live
+    reference's mean row and fit."""
+    from pangenomix_b200 import pangenome_analysis as pa, plot
+    g = load_golden("c2_40000x400")
+    n = int(g["shape"][1])
+    assert g["curves"].shape == (1000, 2 * n)
+    df = pd.DataFrame(g["curves"].astype(np.float64),
+                      columns=["Pan%d" % (i + 1) for i in range(n)] + ["Core%d" % (i + 1) for i in range(n)])
+    mean = plot.calculate_mean(df)
+    assert np.array_equal(mean.values[0], g["mean"])
+    np.testing.assert_allclose(pa.fit_heaps_by_iteration(mean).values[0], g["heaps_mean"], rtol=1e-12)
+    np.testing.assert_allclose(pa.fit_heaps_by_iteration(df.iloc[:8]).values, g["heaps_iter"], rtol=1e-12)
