@@ -4,7 +4,7 @@
 Run in the build container only (the reference does not exist on the GPU box):
 
     python tests/golden/make_golden.py            # the round-1 fixtures
-    python tests/golden/make_golden.py --big      # the full-size fixtures of round 2 (C2, C4, C3; ~3 min)
+    python tests/golden/make_golden.py --big      # the full-size fixtures of round 2 (C2, C4, C3; ~6 min)
     python tests/golden/make_golden.py --betabin  # beta-binomial core estimate, Monte-Carlo KS, gene occurrence
     python tests/golden/make_golden.py --c5       # one permutation of config C5 at full size (tens of minutes)
     python tests/golden/make_golden.py --c3-whole # the reference's Bernoulli fit on the whole table, 40,000 x 400 (minutes)
@@ -134,15 +134,16 @@ def edge_matrix():
 def big_cases(manifest):
     """Round-2 additions: live-reference fixtures at the sizes the performance claims are made on.
 
-    c2_40000x400      config C2 in full, 64 of its 1,000 permutations (the reference needs 0.15 s each)
-    c4_200000x10000   config C4 in full, 4 of its 10,000 permutations (the reference needs ~12 s each)
+    c2_40000x400      config C2 in full: all of its 1,000 permutations (the reference needs 0.1 s each), their mean,
+                      the Heaps fit on the mean
+    c4_200000x10000   config C4 in full, 16 of its 10,000 permutations (the reference needs ~9 s each)
     bernoulli_c3_4000x400  config C3 (candidate-core size): the whole L-BFGS-B fit of the reference (~10 s)
     The matrices are regenerated by pangenomix_b200.synth in the tests and checked against the stored digest.
     """
     c2 = synth.config_matrix("c2")
-    save_curve_case("c2_40000x400", c2, 12345, 64, store_matrix=False, heaps=True)
+    save_curve_case("c2_40000x400", c2, 12345, 1000, store_matrix=False, heaps=True)
     c4 = synth.config_matrix("c4")
-    save_curve_case("c4_200000x10000", c4, 12345, 4, store_matrix=False, heaps=True)
+    save_curve_case("c4_200000x10000", c4, 12345, 16, store_matrix=False, heaps=True)
 
     x, p_true, q_true = synth.bernoulli_grid_matrix(4000, 400, seed=3)
     n_genes, n_genomes = x.shape
