@@ -319,6 +319,17 @@ class LightSparseDataFrame():
         if axis in _COL_AXES:
             return np.asarray(self.data.sum(axis=0)).ravel()
 
+    def sum_gpu(self, axis='index', device=None):
+        """``sum(axis)`` of a BINARY table counted on the GPU (libpgx pgx_coo_marginals_host; SURVEY.md section 8f,
+        rank 4): int64 row sums for axis 'index'/0, column sums for 'columns'/1, equal to what ``sum`` returns.
+        Tables with stored values other than 1 are refused (use ``sum``)."""
+        from .engine import table_marginals
+        row_sum, col_sum, _, _ = table_marginals(self.data, device=device, spectrum=False)
+        if axis in _ROW_AXES:
+            return row_sum
+        if axis in _COL_AXES:
+            return col_sum
+
     def to_npz(self, npz_file, label_file=None):
         """Writes ``npz_file`` (scipy COO, compressed) and the label file
         (default ``<npz_file>.labels.txt``: row labels, then column labels, one per line)."""

@@ -222,6 +222,31 @@ def test_count_gene_occurence_host_logic_matches_reference(oracle_device_calls, 
     assert np.array_equal(again.values, got.values)
 
 
+def _check_sum_gpu_equals_sum(real_device_call):
+    from pangenomix_b200.sparse_utils import LightSparseDataFrame
+    coo = scipy.sparse.coo_matrix(synth.bernoulli_matrix(700, 60, 40, seed=2))
+    index, columns = synth.labels_for(*coo.shape)
+    lsdf = LightSparseDataFrame(np.array(index), np.array(columns), coo)
+    for axis in ("index", 0, "columns", 1):
+        got, want = lsdf.sum_gpu(axis), lsdf.sum(axis)
+        assert got.dtype == np.int64 and np.array_equal(got, want)
+    assert lsdf.sum_gpu("rows") is None and lsdf.sum("rows") is None          # the reference's silent None for other axes
+    if real_device_call:                                   # entries are counted: other values are refused
+        weighted = LightSparseDataFrame(np.array(index), np.array(columns), coo * 2)
+        with pytest.raises(ValueError):
+            weighted.sum_gpu()
+
+
+def test_lsdf_sum_gpu_host_logic(oracle_device_calls):
+    _check_sum_gpu_equals_sum(False)
+
+
+@pytest.mark.gpu
+def test_gpu_lsdf_sum_gpu(cuda):
+    """LightSparseDataFrame.sum_gpu: the marginals of sparse_utils.py:284-292 counted on the device."""
+    _check_sum_gpu_equals_sum(True)
+
+
 def test_drop_in_helpers_match_oracle():
     from pangenomix_b200 import pangenome_analysis as pa
     x = np.arange(40)
